@@ -1,0 +1,206 @@
+"""One training epoch of the learned-sparsifier pipelines, shared by training_hybrid.py and
+training_straight_through.py.  Control flow, branch conditions, optimiser stepping and the
+returned tuple mirror the reference line by line (training_hybrid.py:7-189,
+training_straight_through.py:7-176); the arithmetic runs in libsgs_b200 kernels.
+
+Differences that are deliberate:
+  * host syncs per learned step: ONE 8-scalar D2H for the conditional gate (+ sampler validity
+    flags) and the final loss read, instead of two logits D2H copies + sklearn + two .item();
+  * the hybrid scorer backward touches only the q sampled edges (the only ones with non-zero
+    upstream gradient) instead of all E.
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import ops, sampling
+from .ops import SAMPLE_TRAIN
+
+_softmax_cache = {}
+
+
+def _softmax_prob(prob):
+    """F.softmax(batch.prob) of training_hybrid.py:46, cached per tensor (prob is per-graph)."""
+    key = id(prob)
+    hit = _softmax_cache.get(key)
+    if hit is not None and hit[0]() is prob and hit[1] == prob._version:
+        return hit[2]
+    s = ops.softmax_f32(prob)
+    try:
+        _softmax_cache[key] = (weakref.ref(prob, lambda _r, k=key: _softmax_cache.pop(k, None)), prob._version, s)
+    except TypeError:
+        pass
+    return s
+
+
+def _has_train(batch):
+    flag = getattr(batch, "_sgs_has_train", None)
+    if flag is None:
+        flag = bool(batch.train_mask.any())
+        try:
+            batch._sgs_has_train = flag
+        except Exception:
+            pass
+    return flag
+
+
+def _is_plain_ce(criterion):
+    return (isinstance(criterion, nn.CrossEntropyLoss) and criterion.weight is None
+            and criterion.reduction == "mean" and criterion.label_smoothing == 0.0
+            and criterion.ignore_index == -100)
+
+
+def _ce(criterion, out, batch, tm_u8, acc=None):
+    if _is_plain_ce(criterion):
+        return ops.fused_loss(out, batch.y, tm_u8, acc=acc, reg1=False, reg2=False)
+    return criterion(out[batch.train_mask], batch.y[batch.train_mask])
+
+
+def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, backward_fn):
+    """One learned step on a device-resident batch.  Returns (loss tensor, update_edge_mlp)."""
+    n = batch.x.size(0)
+    g_full = ops.graph_of(batch.edge_index, n)
+    tm_u8 = batch.train_mask.view(torch.uint8)
+    scorer = model.edge_prob_mlp
+    coef = args.degree_bias_coef
+
+    g_rand = None
+    r = None
+    if args.conditional or args.sparse_edge_mlp:
+        # training_hybrid.py:45-48
+        r = sampling.sample_random(_softmax_prob(batch.prob), q, validate=False)
+        g_rand = g_full.subgraph(r.sel)
+
+    # pass 1: probabilities of ALL edges (training_hybrid.py:51-64), no autograd tape
+    profiler = getattr(model, "gpu_profiler", None)
+    if profiler is not None:
+        profiler.begin("edge_mlp_pre")
+    out = scorer.embed(batch.x, g_rand if g_rand is not None else g_full)
+    if profiler is not None:
+        profiler.end("edge_mlp_pre")
+        profiler.begin("edge_score")
+    seed_sc = ops.next_seed()
+    p_drop = scorer._drop()
+    fc1, fc2 = scorer.fc1, scorer.fc2
+    with torch.no_grad():
+        p_full = ops.edge_score_forward(out.detach(), g_full, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
+                                        fc2.bias.reshape(-1), None, p_drop, seed_sc)
+    if profiler is not None:
+        profiler.end("edge_score")
+
+    # sample (training_hybrid.py:72-83)
+    smp = sampling.sample_edges(p_full, batch.prob, q, False, coef, validate=False)
+    g_s = g_full.subgraph(smp.sel)
+    if pipeline == "hybrid":
+        # edge_probs_full[mask] with grad (training_hybrid.py:86): backward over the q edges only
+        p_sel = ops.gather_selected(p_full, None, smp.sel, ops.SAMPLE_RAW, 0.0, None)[0]
+        p_s = scorer.score(out, g_full, ids=smp.sel, precomputed=p_sel, seed=seed_sc)
+    elif pipeline == "straight_through":
+        # sampled_edge_weight = (p * st)[mask].clamp(0,1) with dense gradient
+        # (training_straight_through.py:60-75, sampling.py:137-155)
+        p_full_g = scorer.score(out, g_full, precomputed=p_full, seed=seed_sc)
+        p_s = ops.StraightThroughWeightsFn.apply(p_full_g, batch.prob, smp.sel, smp.S, SAMPLE_TRAIN, coef)
+    else:
+        raise ValueError(pipeline)
+
+    learned_out = model(batch, g_s, p_s)
+
+    update_edge_mlp = True
+    acc_l = acc_r = None
+    random_out = None
+    with_edges = bool(args.reg1 or args.reg2)
+    if args.conditional:
+        random_out = model(batch, g_rand)
+        # calculate_f1 x2 (training_hybrid.py:94-95): micro-F1 == accuracy; same denominator, so the
+        # strict `>` of :98 compares the two correct-counts.
+        acc_l = ops.loss_forward(learned_out.detach(), batch.y, tm_u8, g_s if with_edges else None,
+                                 p_s.detach() if with_edges else None)
+        acc_r = ops.loss_forward(random_out.detach(), batch.y, tm_u8)
+        host = torch.cat([acc_l, acc_r, smp.state.double(), r.state.double()]).cpu()
+        _check_sampler(host[16:24], q)
+        _check_sampler(host[24:32], q)
+        update_edge_mlp = bool(host[2] > host[8 + 2])
+    if update_edge_mlp:
+        loss = ops.fused_loss(learned_out, batch.y, tm_u8, p_s if with_edges else None, g_s if with_edges else None,
+                              args.regularizer1_coef, args.consist_reg_coef, bool(args.reg1), bool(args.reg2),
+                              acc=acc_l)
+    else:
+        loss = _ce(criterion, random_out, batch, tm_u8, acc_r)
+    backward_fn(loss)
+    return loss, update_edge_mlp
+
+
+def _check_sampler(st, q):
+    if int(st[5]) != 0:
+        raise RuntimeError("probability tensor contains either `inf`, `nan` or element < 0")
+    if int(st[7]) != q:
+        raise RuntimeError(f"sampler selected {int(st[7])} edges, expected {q}")
+
+
+def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimizer_edge_prob, optimizer, criterion,
+                cluster_loader, q=500, alternate_frequency=1):
+    device = args.device
+    mode = args.mode
+    model.train()
+    profiler = getattr(model, "gpu_profiler", None)
+    total_loss = 0
+    temperature = 1.0
+    conditional_update = 0
+    total_update = 0
+
+    def _backward(loss):
+        if profiler is not None:
+            profiler.begin("backward")
+        loss.backward()
+        if profiler is not None:
+            profiler.end("backward")
+
+    for batch in cluster_loader:
+        if not _has_train(batch):
+            continue
+        total_update += 1
+        optimizer_edge_prob.zero_grad()
+        optimizer_gnn.zero_grad()
+
+        if mode == "learned":
+            if batch.edge_index.shape[1] > q:
+                batch = batch.to(device)
+                # temperature anneal: computed and returned, never used by the sampler
+                # (training_hybrid.py:67-70)
+                r_ = (args.t_init - args.t_min) / max_epoch
+                temperature = max(args.t_min, args.t_init - epoch * r_)
+                loss, update_edge_mlp = learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q,
+                                                     _backward)
+                if update_edge_mlp:
+                    conditional_update += 1
+                    optimizer_edge_prob.step()
+                    optimizer_gnn.step()
+                else:
+                    optimizer_gnn.step()
+            else:
+                batch = batch.to(device)
+                out = model(batch, batch.edge_index)
+                loss = _ce(criterion, out, batch, batch.train_mask.view(torch.uint8))
+                _backward(loss)
+                optimizer_gnn.step()
+        elif mode in ("random", "edge", "full"):
+            batch = batch.to(device)
+            ei = batch.edge_index
+            if mode == "random" and ei.shape[1] > q:
+                ei = sampling.random_edge_sampling(ei, q=q)
+            elif mode == "edge" and ei.shape[1] > q:
+                g_full = ops.graph_of(batch.edge_index, batch.x.size(0))
+                ei = g_full.subgraph(sampling.sample_random(_softmax_prob(batch.prob), q).sel)
+            out = model(batch, ei)
+            loss = _ce(criterion, out, batch, batch.train_mask.view(torch.uint8))
+            _backward(loss)
+            optimizer.step()
+        else:
+            raise ValueError("Invalid mode. Choose 'learned', 'random', or 'full'.")
+
+        total_loss += loss.item()
+
+    return total_loss / len(cluster_loader), temperature, conditional_update, total_update

@@ -1,0 +1,101 @@
+// Shared helpers for libsgs_b200 (sm_100a).  Internal -- the public surface is include/sgs_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sgs_b200.h"
+
+namespace sgs {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SGS_CHECK_ARG(cond, msg)                           \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      sgs::set_error("%s: %s", __func__, msg);             \
+      return SGS_E_INVALID;                                \
+    }                                                      \
+  } while (0)
+
+#define SGS_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      sgs::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return SGS_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define SGS_LAUNCH_CHECK()                 \
+  do {                                     \
+    sgs::count_launch();                   \
+    SGS_CUDA(cudaPeekAtLastError());       \
+  } while (0)
+
+static inline cudaStream_t as_stream(sgs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------
+// Counter-based hash RNG (splitmix64 finaliser).  Dropout keep decisions are a pure function
+// of (seed, row, column) so that forward and backward kernels (and the numpy mirror in
+// sgs_gnn_b200/rng.py used by the parity tests) regenerate the same mask.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// 64 random bits for the 4 consecutive columns [4*col4, 4*col4+4) of `row`.
+__host__ __device__ __forceinline__ uint64_t dropout_bits(uint64_t seed, uint64_t row, uint32_t col4) {
+  return splitmix64(seed ^ splitmix64((row << 20) | (uint64_t)col4));
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  float t = p * 65536.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65536.f ? 65536u : (uint32_t)t);
+}
+// keep column (4*col4 + k) iff its 16-bit lane >= threshold
+__host__ __device__ __forceinline__ bool dropout_keep(uint64_t bits, int k, uint32_t thr) {
+  return ((uint32_t)(bits >> (16 * k)) & 0xFFFFu) >= thr;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// streaming 128-bit load that does not pollute L1 (data read exactly once)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+#endif
+
+}  // namespace sgs

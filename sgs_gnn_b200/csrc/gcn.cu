@@ -1,0 +1,407 @@
+// K3: gcn_norm, CSR SpMM (forward, and backward via the by-source CSR), activation backward,
+// bias gradient and the edge-weight gradient (SDDMM + per-node sums).
+// All segment reductions are atomic-free: one warp owns one CSR row.
+#include "common.cuh"
+
+namespace sgs {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlock = kWarpsPerBlock * 32;
+
+// ---------------------------------------------------------------------------------------
+// gcn_norm phase 1: weighted in-degree with "remaining" self loops.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+gcn_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                  const int32_t* __restrict__ nbr, const float* __restrict__ w, int64_t N,
+                  float* __restrict__ deg, float* __restrict__ dis, float* __restrict__ loopw) {
+  int lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int64_t nrows_step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; row < N; row += nrows_step) {
+    int beg = rowptr[row], end = rowptr[row + 1];
+    float acc = 0.f;
+    int loop_e = -1;  // highest edge id among input self loops (CPU "last write wins")
+    for (int i = beg + lane; i < end; i += 32) {
+      int s = nbr[i];
+      int e = perm[i];
+      if (s == (int)row) {
+        loop_e = max(loop_e, e);
+      } else {
+        acc += w ? w[e] : 1.0f;
+      }
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loop_e = max(loop_e, __shfl_xor_sync(0xffffffffu, loop_e, o));
+    if (lane == 0) {
+      float lw = (loop_e >= 0 && w) ? w[loop_e] : 1.0f;
+      float d = acc + lw;
+      float r = 1.0f / sqrtf(d);
+      if (isinf(r)) r = 0.f;
+      deg[row] = d;
+      dis[row] = r;
+      loopw[row] = lw;
+    }
+  }
+}
+
+// phase 2: what[i] = (dis[nbr] * w) * dis[row]   (0 for input self loops)
+__global__ void __launch_bounds__(kBlock)
+gcn_what_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                const int32_t* __restrict__ nbr, const float* __restrict__ w,
+                const float* __restrict__ dis, int64_t N, float* __restrict__ what) {
+  int lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; row < N; row += step) {
+    int beg = rowptr[row], end = rowptr[row + 1];
+    float dr = dis[row];
+    for (int i = beg + lane; i < end; i += 32) {
+      int s = nbr[i];
+      float we = w ? w[perm[i]] : 1.0f;
+      what[i] = (s == (int)row) ? 0.f : (dis[s] * we) * dr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SpMM: out[r, cols] = act(sum_i what[i] * h[nbr[i], cols] + selfw * h[r, cols] + bias)
+// A warp owns a row; each lane owns K chunks of VEC consecutive columns:
+//   col(k, lane) = col0 + (k * 32 + lane) * VEC.
+// (nbr, what) pairs are fetched 32 at a time (coalesced) and broadcast with shuffles so the
+// feature-row loads of consecutive neighbours are independent and stay in flight together.
+// ---------------------------------------------------------------------------------------
+template <int VEC, int K>
+__global__ void __launch_bounds__(kBlock)
+spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+            const float* __restrict__ what, const float* __restrict__ dis,
+            const float* __restrict__ loopw, const float* __restrict__ h, int64_t N, int D,
+            const float* __restrict__ bias, float* __restrict__ out, int flags, float p_drop,
+            uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * (32 * VEC * K);
+  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  const uint32_t thr = dropout_threshold(p_drop);
+  const float scale = (flags & SGS_SPMM_DROPOUT) ? 1.0f / (1.0f - p_drop) : 1.0f;
+
+  for (; row < N; row += step) {
+    float acc[K][VEC];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
+
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    for (int base = beg; base < end; base += 32) {
+      int my_n = 0;
+      float my_w = 0.f;
+      if (base + lane < end) {
+        my_n = nbr[base + lane];
+        my_w = what[base + lane];
+      }
+      const int cnt = min(32, end - base);
+#pragma unroll 4
+      for (int j = 0; j < cnt; ++j) {
+        const int n = __shfl_sync(0xffffffffu, my_n, j);
+        const float wv = __shfl_sync(0xffffffffu, my_w, j);
+        const float* hp = h + (int64_t)n * D;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = col0 + (k * 32 + lane) * VEC;
+          if (c < D) {
+            if (VEC == 4) {
+              const float4 x = *reinterpret_cast<const float4*>(hp + c);
+              acc[k][0] = fmaf(wv, x.x, acc[k][0]);
+              acc[k][1] = fmaf(wv, x.y, acc[k][1]);
+              acc[k][2] = fmaf(wv, x.z, acc[k][2]);
+              acc[k][3] = fmaf(wv, x.w, acc[k][3]);
+            } else {
+              acc[k][0] = fmaf(wv, hp[c], acc[k][0]);
+            }
+          }
+        }
+      }
+    }
+    // self loop, bias, activation
+    float selfw = 0.f;
+    if (dis) {
+      const float d = dis[row];
+      selfw = d * d * (loopw ? loopw[row] : 1.0f);
+    }
+    const float* hr = h + row * D;
+    float* orow = out + row * D;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = col0 + (k * 32 + lane) * VEC;
+      if (c < D) {
+        float v[VEC];
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) {
+          v[t] = acc[k][t];
+          if (dis) v[t] = fmaf(selfw, hr[c + t], v[t]);
+          if (bias) v[t] += bias[c + t];
+          if (flags & SGS_SPMM_RELU) v[t] = fmaxf(v[t], 0.f);
+        }
+        if (flags & SGS_SPMM_DROPOUT) {
+          const uint64_t bits = dropout_bits(seed, (uint64_t)row, (uint32_t)(c >> 2));
+#pragma unroll
+          for (int t = 0; t < VEC; ++t)
+            v[t] = dropout_keep(bits, (c + t) & 3, thr) ? v[t] * scale : 0.f;
+        }
+        if (flags & SGS_SPMM_ACCUM) {
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) v[t] += orow[c + t];
+        }
+        if (VEC == 4) {
+          *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          orow[c] = v[0];
+        }
+      }
+    }
+  }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, int64_t n,
+                               float scale, float* __restrict__ gin) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) gin[i] = out[i] > 0.f ? gout[i] * scale : 0.f;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ G, int64_t N, int D, float* __restrict__ cs) {
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t r = blockIdx.x; r < N; r += gridDim.x) acc += G[r * D + c];
+    atomicAdd(cs + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Edge-weight gradient.  Phase A: SDDMM over by-dst rows + dst-side sums.
+// ---------------------------------------------------------------------------------------
+template <int VEC, int K>
+__global__ void __launch_bounds__(kBlock)
+edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                       const int32_t* __restrict__ nbr, const float* __restrict__ what,
+                       const float* __restrict__ G, const float* __restrict__ h,
+                       const float* __restrict__ dis, const float* __restrict__ loopw, int64_t N, int D,
+                       float* __restrict__ tmp_g, float* __restrict__ tmp_t, float* __restrict__ tmp_a) {
+  const int lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; row < N; row += step) {
+    float g_row[K][VEC];
+    const float* gr = G + row * D;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * 32 + lane) * VEC;
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) g_row[k][t] = (c + t < D) ? gr[c + t] : 0.f;
+    }
+    auto dot_with = [&](const float* hp) {
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int c = (k * 32 + lane) * VEC;
+        if (c < D) {
+          if (VEC == 4) {
+            const float4 x = *reinterpret_cast<const float4*>(hp + c);
+            d = fmaf(g_row[k][0], x.x, d);
+            d = fmaf(g_row[k][1], x.y, d);
+            d = fmaf(g_row[k][2], x.z, d);
+            d = fmaf(g_row[k][3], x.w, d);
+          } else {
+            d = fmaf(g_row[k][0], hp[c], d);
+          }
+        }
+      }
+      return warp_sum(d);
+    };
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    float tsum = 0.f;
+    for (int i = beg; i < end; ++i) {
+      const int s = nbr[i];
+      const float g = dot_with(h + (int64_t)s * D);
+      if (lane == 0) {
+        const int e = perm[i];
+        const float t = g * what[i];
+        tmp_g[e] = g;
+        tmp_t[e] = t;
+        tsum += t;
+      }
+    }
+    const float gl = dot_with(h + row * D);
+    if (lane == 0) {
+      const float d = dis[row];
+      const float tl = gl * d * d * loopw[row];
+      tmp_a[row] = tsum + 2.0f * tl;
+    }
+  }
+}
+
+// Phase B: add the source-side sums  A[r] += sum_{e: src_e = r} t_e
+__global__ void __launch_bounds__(kBlock)
+edge_grad_srcsum_kernel(const int32_t* __restrict__ rowptr_src, const int32_t* __restrict__ perm_src,
+                        const float* __restrict__ tmp_t, int64_t N, float* __restrict__ tmp_a) {
+  const int lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; row < N; row += step) {
+    const int beg = rowptr_src[row], end = rowptr_src[row + 1];
+    float acc = 0.f;
+    for (int i = beg + lane; i < end; i += 32) acc += tmp_t[perm_src[i]];
+    acc = warp_sum(acc);
+    if (lane == 0) tmp_a[row] += acc;
+  }
+}
+
+// Phase C: dL/dw_e = g_e dis[r] dis[c] - A_c / (2 deg_c)
+__global__ void edge_grad_final_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                       const float* __restrict__ tmp_g, const float* __restrict__ tmp_a,
+                                       const float* __restrict__ dis, const float* __restrict__ deg,
+                                       int64_t M, float* __restrict__ dw, int accumulate) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < M; e += stride) {
+    const int r = src[e], c = dst[e];
+    float v = 0.f;
+    if (r != c) v = tmp_g[e] * dis[r] * dis[c] - tmp_a[c] / (2.0f * deg[c]);
+    dw[e] = accumulate ? dw[e] + v : v;
+  }
+}
+
+static inline int row_grid(int64_t N) {
+  int64_t g = ceil_div(N, kWarpsPerBlock);
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sgs
+
+using namespace sgs;
+
+extern "C" {
+
+int32_t sgs_gcn_norm(const int32_t* rowptr, const int32_t* perm, const int32_t* nbr, const float* w,
+                     int64_t M, int64_t N, float* deg, float* dis, float* loopw, float* what,
+                     sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && M >= 0, "bad sizes");
+  SGS_CHECK_ARG(rowptr && deg && dis && loopw && (M == 0 || (perm && nbr && what)), "null pointer");
+  cudaStream_t st = as_stream(stream);
+  gcn_degree_kernel<<<row_grid(N), kBlock, 0, st>>>(rowptr, perm, nbr, w, N, deg, dis, loopw);
+  SGS_LAUNCH_CHECK();
+  if (M > 0) {
+    gcn_what_kernel<<<row_grid(N), kBlock, 0, st>>>(rowptr, perm, nbr, w, dis, N, what);
+    SGS_LAUNCH_CHECK();
+  }
+  return SGS_OK;
+}
+
+int32_t sgs_gcn_norm_apply(const int32_t* rowptr, const int32_t* perm, const int32_t* nbr, const float* w,
+                           const float* dis, int64_t M, int64_t N, float* what, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && M >= 0, "bad sizes");
+  if (M == 0) return SGS_OK;
+  SGS_CHECK_ARG(rowptr && perm && nbr && dis && what, "null pointer");
+  gcn_what_kernel<<<row_grid(N), kBlock, 0, as_stream(stream)>>>(rowptr, perm, nbr, w, dis, N, what);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, const float* dis,
+                 const float* loopw, const float* h, int64_t N, int64_t D, const float* bias, float* out,
+                 int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && D > 0 && D < (1 << 20), "bad sizes");
+  SGS_CHECK_ARG(rowptr && h && out, "null pointer");
+  SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
+  if ((flags & SGS_SPMM_DROPOUT) && p_drop == 0.f) flags &= ~SGS_SPMM_DROPOUT;
+  cudaStream_t st = as_stream(stream);
+  const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)out) % 16 == 0);
+  dim3 block(kBlock);
+#define SGS_SPMM_LAUNCH(VEC, K)                                                                        \
+  do {                                                                                                 \
+    dim3 grid(row_grid(N), (unsigned)ceil_div(D, 32 * VEC * K));                                       \
+    spmm_kernel<VEC, K><<<grid, block, 0, st>>>(rowptr, nbr, what, dis, loopw, h, N, (int)D, bias, out, \
+                                                flags, p_drop, seed);                                  \
+  } while (0)
+  if (vec4) {
+    if (D <= 128) SGS_SPMM_LAUNCH(4, 1);
+    else if (D <= 256) SGS_SPMM_LAUNCH(4, 2);
+    else SGS_SPMM_LAUNCH(4, 4);
+  } else {
+    if (D <= 32) SGS_SPMM_LAUNCH(1, 1);
+    else if (D <= 64) SGS_SPMM_LAUNCH(1, 2);
+    else SGS_SPMM_LAUNCH(1, 4);
+  }
+#undef SGS_SPMM_LAUNCH
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_act_bwd(const float* gout, const float* out, int64_t n, float scale, float* gin,
+                    sgs_stream_t stream) {
+  SGS_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return SGS_OK;
+  SGS_CHECK_ARG(gout && out && gin, "null pointer");
+  int64_t g = ceil_div(n, 256);
+  int64_t cap = (int64_t)sm_count() * 16;
+  act_bwd_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, as_stream(stream)>>>(gout, out, n, scale, gin);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_colsum(const float* G, int64_t N, int64_t D, float* colsum, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N >= 0 && D > 0, "bad sizes");
+  SGS_CHECK_ARG(G && colsum, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  SGS_CUDA(cudaMemsetAsync(colsum, 0, D * sizeof(float), st));
+  if (N == 0) return SGS_OK;
+  int64_t g = N < (int64_t)sm_count() * 4 ? N : (int64_t)sm_count() * 4;
+  colsum_kernel<<<(unsigned)g, 256, 0, st>>>(G, N, (int)D, colsum);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
+                          const float* what_dst, const int32_t* rowptr_src, const int32_t* perm_src,
+                          const int32_t* src, const int32_t* dst, const float* G, const float* h,
+                          const float* dis, const float* deg, const float* loopw, int64_t M, int64_t N,
+                          int64_t D, float* tmp_g, float* tmp_t, float* tmp_a, float* dw, int32_t accumulate,
+                          sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && M >= 0 && D > 0, "bad sizes");
+  if (M == 0) return SGS_OK;
+  SGS_CHECK_ARG(rowptr_dst && perm_dst && nbr_dst && what_dst && rowptr_src && perm_src && src && dst && G &&
+                    h && dis && deg && loopw && tmp_g && tmp_t && tmp_a && dw,
+                "null pointer");
+  cudaStream_t st = as_stream(stream);
+  const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)G) % 16 == 0);
+#define SGS_SDDMM_LAUNCH(VEC, K)                                                                         \
+  edge_grad_sddmm_kernel<VEC, K><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, \
+                                                                 G, h, dis, loopw, N, (int)D, tmp_g, tmp_t, \
+                                                                 tmp_a)
+  if (vec4 && D <= 128) SGS_SDDMM_LAUNCH(4, 1);
+  else if (vec4 && D <= 256) SGS_SDDMM_LAUNCH(4, 2);
+  else if (vec4 && D <= 512) SGS_SDDMM_LAUNCH(4, 4);
+  else if (vec4 && D <= 1024) SGS_SDDMM_LAUNCH(4, 8);
+  else if (D <= 32) SGS_SDDMM_LAUNCH(1, 1);
+  else if (D <= 64) SGS_SDDMM_LAUNCH(1, 2);
+  else if (D <= 128) SGS_SDDMM_LAUNCH(1, 4);
+  else if (D <= 256) SGS_SDDMM_LAUNCH(1, 8);
+  else {
+    set_error("sgs_gcn_edge_grad: unsupported width %lld", (long long)D);
+    return SGS_E_UNSUPPORTED;
+  }
+#undef SGS_SDDMM_LAUNCH
+  SGS_LAUNCH_CHECK();
+  edge_grad_srcsum_kernel<<<row_grid(N), kBlock, 0, st>>>(rowptr_src, perm_src, tmp_t, N, tmp_a);
+  SGS_LAUNCH_CHECK();
+  int64_t g = ceil_div(M, 256);
+  int64_t cap = (int64_t)sm_count() * 16;
+  edge_grad_final_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(src, dst, tmp_g, tmp_a, dis, deg, M, dw,
+                                                                        accumulate);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+}

@@ -1,0 +1,157 @@
+// Graph preparation: int64 COO -> int32, column gathers, CSR (by dst / by src) construction.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace sgs {
+
+__global__ void edge_index_split_kernel(const int64_t* __restrict__ ei, int64_t M, int64_t N,
+                                        int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                        int32_t* __restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < M; i += stride) {
+    int64_t s = ei[i], d = ei[M + i];
+    bad |= (s < 0) | (s >= N) | (d < 0) | (d >= N);
+    src[i] = (int32_t)s;
+    dst[i] = (int32_t)d;
+  }
+  if (bad) *err = 1;
+}
+
+__global__ void edge_index_gather_kernel(const int64_t* __restrict__ ei, int64_t M,
+                                         const int32_t* __restrict__ ids, int64_t q,
+                                         int64_t* __restrict__ out, int32_t* __restrict__ so,
+                                         int32_t* __restrict__ dout) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < q; i += stride) {
+    int64_t e = ids[i];
+    int64_t s = ei[e], d = ei[M + e];
+    if (out) {
+      out[i] = s;
+      out[q + i] = d;
+    }
+    if (so) so[i] = (int32_t)s;
+    if (dout) dout[i] = (int32_t)d;
+  }
+}
+
+__global__ void iota_copy_kernel(const int32_t* __restrict__ key, int64_t M, int32_t* __restrict__ kout,
+                                 int32_t* __restrict__ vout) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < M; i += stride) {
+    kout[i] = key[i];
+    vout[i] = (int32_t)i;
+  }
+}
+
+// rowptr[k] = first position in the sorted key array with key >= k   (k in [0, N])
+__global__ void rowptr_kernel(const int32_t* __restrict__ sorted, int64_t M, int64_t N,
+                              int32_t* __restrict__ rowptr) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > N) return;
+  int64_t lo = 0, hi = M;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted[mid] < (int32_t)k) lo = mid + 1; else hi = mid;
+  }
+  rowptr[k] = (int32_t)lo;
+}
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx,
+                                  int64_t M, int32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < M; i += stride) out[i] = src[idx[i]];
+}
+
+static inline int grid_for(int64_t n, int block, int waves = 8) {
+  int64_t g = ceil_div(n, block);
+  int64_t cap = (int64_t)sm_count() * waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static size_t cub_temp_bound(int64_t M) { return (size_t)(32u << 20) + (size_t)(M / 8) * 4; }
+
+}  // namespace sgs
+
+using namespace sgs;
+
+extern "C" {
+
+int32_t sgs_edge_index_split(const int64_t* edge_index, int64_t M, int64_t N, int32_t* src,
+                             int32_t* dst, int32_t* err_flag, sgs_stream_t stream) {
+  SGS_CHECK_ARG(M >= 0 && N >= 0 && N < (1ll << 31) && M < (1ll << 31), "M, N must fit int32");
+  SGS_CHECK_ARG(M == 0 || (edge_index && src && dst && err_flag), "null pointer");
+  if (M == 0) return SGS_OK;
+  edge_index_split_kernel<<<grid_for(M, 256), 256, 0, as_stream(stream)>>>(edge_index, M, N, src, dst,
+                                                                           err_flag);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_edge_index_gather(const int64_t* edge_index, int64_t M, const int32_t* ids, int64_t q,
+                              int64_t* out, int32_t* src_out, int32_t* dst_out, sgs_stream_t stream) {
+  SGS_CHECK_ARG(q >= 0 && M >= 0, "negative size");
+  if (q == 0) return SGS_OK;
+  SGS_CHECK_ARG(edge_index && ids, "null pointer");
+  edge_index_gather_kernel<<<grid_for(q, 256), 256, 0, as_stream(stream)>>>(edge_index, M, ids, q, out,
+                                                                            src_out, dst_out);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+size_t sgs_csr_workspace_bytes(int64_t M, int64_t N) {
+  (void)N;
+  size_t m = (size_t)(M > 0 ? M : 1);
+  return 4 * m * sizeof(int32_t) + 1024 + cub_temp_bound(M);
+}
+
+int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64_t N, int32_t* rowptr,
+                      int32_t* perm, int32_t* nbr, void* ws, size_t ws_bytes, sgs_stream_t stream) {
+  SGS_CHECK_ARG(M >= 0 && N > 0, "bad sizes");
+  SGS_CHECK_ARG(rowptr != nullptr, "null rowptr");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) {
+    SGS_CUDA(cudaMemsetAsync(rowptr, 0, (N + 1) * sizeof(int32_t), st));
+    return SGS_OK;
+  }
+  SGS_CHECK_ARG(key && other && perm && nbr && ws, "null pointer");
+  if (ws_bytes < sgs_csr_workspace_bytes(M, N)) {
+    set_error("sgs_csr_build: workspace too small");
+    return SGS_E_WORKSPACE;
+  }
+  int32_t* kA = (int32_t*)ws;
+  int32_t* kB = kA + M;
+  int32_t* vA = kB + M;
+  int32_t* vB = vA + M;
+  char* temp = (char*)(vB + M);
+  temp = (char*)(((uintptr_t)temp + 255) & ~(uintptr_t)255);
+  size_t temp_avail = ws_bytes - (size_t)(temp - (char*)ws);
+  iota_copy_kernel<<<grid_for(M, 256), 256, 0, st>>>(key, M, kA, vA);
+  SGS_LAUNCH_CHECK();
+  int end_bit = 1;
+  while (end_bit < 31 && (1ll << end_bit) < N) ++end_bit;
+  cub::DoubleBuffer<int32_t> dk(kA, kB);
+  cub::DoubleBuffer<int32_t> dv(vA, vB);
+  size_t need = 0;
+  SGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)M, 0, end_bit, st));
+  if (need > temp_avail) {
+    set_error("sgs_csr_build: cub temp %zu > available %zu", need, temp_avail);
+    return SGS_E_WORKSPACE;
+  }
+  SGS_CUDA(cub::DeviceRadixSort::SortPairs(temp, need, dk, dv, (int)M, 0, end_bit, st));
+  count_launch(4);
+  rowptr_kernel<<<(unsigned)ceil_div(N + 1, 256), 256, 0, st>>>(dk.Current(), M, N, rowptr);
+  SGS_LAUNCH_CHECK();
+  SGS_CUDA(cudaMemcpyAsync(perm, dv.Current(), M * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  gather_i32_kernel<<<grid_for(M, 256), 256, 0, st>>>(other, dv.Current(), M, nbr);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+}

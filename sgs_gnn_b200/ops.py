@@ -1,0 +1,587 @@
+"""Thin PyTorch-facing wrappers over the C ABI (include/sgs_b200.h): tensor validation,
+workspace allocation with torch's caching allocator, and the autograd.Functions that give the
+reference's modules their backward.  PyTorch is plumbing here (device memory, streams,
+autograd bookkeeping); every arithmetic step is a libsgs_b200 kernel.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (PREC_BF16, PREC_FP16, PREC_FP32, PREC_TF32, SAMPLE_RAW, SAMPLE_TEST, SAMPLE_TRAIN,
+                   SPMM_ACCUM, SPMM_DROPOUT, SPMM_RELU, check, lib)
+
+# ------------------------------------------------------------------------------------------
+# configuration
+# ------------------------------------------------------------------------------------------
+_PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "tf32": PREC_TF32}
+_state = {"gemm": PREC_FP32, "scorer": PREC_FP32}
+
+
+def set_precision(gemm=None, scorer=None):
+    """Precision of the dense contractions: 'fp32' (CUDA cores, parity mode) or a tcgen05
+    tensor-core mode ('bf16' / 'fp16' / 'tf32')."""
+    if gemm is not None:
+        _state["gemm"] = _PRECISION[gemm] if isinstance(gemm, str) else int(gemm)
+    if scorer is not None:
+        _state["scorer"] = _PRECISION[scorer] if isinstance(scorer, str) else int(scorer)
+
+
+def get_precision():
+    inv = {v: k for k, v in _PRECISION.items()}
+    return {k: inv[v] for k, v in _state.items()}
+
+
+_seed_counter = itertools.count(1)
+
+
+def next_seed():
+    """Counter-based seed for dropout masks / sampler noise, derived from torch's seed so that
+    utils.fix_seeds() makes runs reproducible."""
+    base = torch.initial_seed() & 0xFFFFFFFFFFFF
+    return (base * 0x9E3779B1 + next(_seed_counter) * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+
+
+def reset_seed_counter():
+    global _seed_counter
+    _seed_counter = itertools.count(1)
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (sgs_gnn_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# graph structure
+# ------------------------------------------------------------------------------------------
+
+class GcnNorm:
+    """deg / dis / loop weights and the normalised edge weights in both CSR orders."""
+
+    __slots__ = ("deg", "dis", "loopw", "what_dst", "_what_src", "_graph", "_w")
+
+    def __init__(self, graph, w):
+        dev = graph.device
+        n, m = graph.num_nodes, graph.num_edges
+        rowptr, perm, nbr = graph.csr_dst
+        self.deg = torch.empty(n, dtype=torch.float32, device=dev)
+        self.dis = torch.empty_like(self.deg)
+        self.loopw = torch.empty_like(self.deg)
+        self.what_dst = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        check(lib().sgs_gcn_norm(_p(rowptr), _p(perm), _p(nbr), _p(w), m, n, _p(self.deg), _p(self.dis),
+                                 _p(self.loopw), _p(self.what_dst), _stream()), "sgs_gcn_norm")
+        self._what_src = None
+        self._graph = graph
+        self._w = w
+
+    @property
+    def what_src(self):
+        if self._what_src is None:
+            g = self._graph
+            rowptr, perm, nbr = g.csr_src
+            self._what_src = torch.empty(max(g.num_edges, 1), dtype=torch.float32, device=g.device)
+            check(lib().sgs_gcn_norm_apply(_p(rowptr), _p(perm), _p(nbr), _p(self._w), _p(self.dis),
+                                           g.num_edges, g.num_nodes, _p(self._what_src), _stream()),
+                  "sgs_gcn_norm_apply")
+        return self._what_src
+
+
+class Graph:
+    """An edge list narrowed to int32 with lazily built CSR-by-destination (forward SpMM) and
+    CSR-by-source (backward SpMM) views, and cached gcn_norm results."""
+
+    def __init__(self, src, dst, num_nodes, edge_index=None):
+        self.src = src
+        self.dst = dst
+        self.num_nodes = int(num_nodes)
+        self.num_edges = int(src.numel())
+        self.device = src.device
+        self.edge_index = edge_index
+        self._csr_dst = None
+        self._csr_src = None
+        self._norm_unw = None
+        self._norm_w = None  # (weakref to weight tensor, version, GcnNorm)
+
+    @staticmethod
+    def from_edge_index(edge_index, num_nodes, validate=False):
+        ei = _req(edge_index, torch.int64, "edge_index")
+        if ei.dim() != 2 or ei.size(0) != 2:
+            raise RuntimeError("edge_index must have shape [2, E]")
+        m = ei.size(1)
+        src = torch.empty(m, dtype=torch.int32, device=ei.device)
+        dst = torch.empty_like(src)
+        flag = torch.zeros(1, dtype=torch.int32, device=ei.device)
+        check(lib().sgs_edge_index_split(_p(ei), m, int(num_nodes), _p(src), _p(dst), _p(flag), _stream()),
+              "sgs_edge_index_split")
+        if validate and int(flag.item()) != 0:
+            raise RuntimeError("edge_index contains node ids outside [0, num_nodes)")
+        return Graph(src, dst, num_nodes, ei)
+
+    def subgraph(self, ids, want_edge_index=False):
+        """Edge-induced subgraph on edge ids (int32 [q]); optionally also the int64 [2,q] tensor."""
+        q = int(ids.numel())
+        src = torch.empty(q, dtype=torch.int32, device=self.device)
+        dst = torch.empty_like(src)
+        out = torch.empty(2, q, dtype=torch.int64, device=self.device) if want_edge_index else None
+        if self.edge_index is not None:
+            check(lib().sgs_edge_index_gather(_p(self.edge_index), self.num_edges, _p(ids), q, _p(out), _p(src),
+                                              _p(dst), _stream()), "sgs_edge_index_gather")
+        else:
+            idl = ids.long()
+            src, dst = self.src[idl].contiguous(), self.dst[idl].contiguous()
+            if want_edge_index:
+                out = torch.stack([src.long(), dst.long()])
+        return Graph(src, dst, self.num_nodes, out)
+
+    def _build(self, key, other):
+        n, m = self.num_nodes, self.num_edges
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
+        perm = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
+        nbr = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
+        nbytes = lib().sgs_csr_workspace_bytes(m, n)
+        ws = _ws(nbytes, self.device)
+        check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(ws), ws.numel(),
+                                  _stream()), "sgs_csr_build")
+        return rowptr, perm, nbr
+
+    @property
+    def csr_dst(self):
+        if self._csr_dst is None:
+            self._csr_dst = self._build(self.dst, self.src)
+        return self._csr_dst
+
+    @property
+    def csr_src(self):
+        if self._csr_src is None:
+            self._csr_src = self._build(self.src, self.dst)
+        return self._csr_src
+
+    def norm(self, edge_weight=None):
+        if edge_weight is None:
+            if self._norm_unw is None:
+                self._norm_unw = GcnNorm(self, None)
+            return self._norm_unw
+        w = edge_weight.detach()
+        c = self._norm_w
+        if c is not None and c[0]() is edge_weight and c[1] == edge_weight._version:
+            return c[2]
+        w = _req(w, torch.float32, "edge_weight")
+        if w.numel() != self.num_edges:
+            raise RuntimeError("edge_weight must have one entry per edge")
+        nrm = GcnNorm(self, w)
+        self._norm_w = (weakref.ref(edge_weight), edge_weight._version, nrm)
+        return nrm
+
+
+_graph_cache = {}
+
+
+def graph_of(edge_index, num_nodes):
+    """Graph for an int64 [2,E] tensor, cached on the tensor's identity + version (the way PyG
+    caches normalisation), evicted when the tensor dies."""
+    if isinstance(edge_index, Graph):
+        return edge_index
+    key = id(edge_index)
+    hit = _graph_cache.get(key)
+    if hit is not None and hit[0]() is edge_index and hit[1] == edge_index._version and hit[2].num_nodes == num_nodes:
+        return hit[2]
+    g = Graph.from_edge_index(edge_index, num_nodes)
+    try:
+        ref = weakref.ref(edge_index, lambda _r, k=key: _graph_cache.pop(k, None))
+        _graph_cache[key] = (ref, edge_index._version, g)
+    except TypeError:
+        pass
+    return g
+
+
+# ------------------------------------------------------------------------------------------
+# dense contraction
+# ------------------------------------------------------------------------------------------
+
+def gemm(a, a_sm, a_sk, b, b_sn, b_sk, m, n, k, out=None, accumulate=False, precision=None):
+    """out[m,n] (+)= sum_k A(m,k) B(n,k) with explicit element strides (include/sgs_b200.h K4)."""
+    prec = _state["gemm"] if precision is None else precision
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    check(lib().sgs_gemm(_p(a), a_sm, a_sk, _p(b), b_sn, b_sk, _p(out), out.stride(0), m, n, k,
+                         1 if accumulate else 0, prec, _stream()), "sgs_gemm")
+    return out
+
+
+def linear_nt(x, w, precision=None):
+    """x[M,K] @ w[N,K]^T"""
+    x = _req(x, torch.float32, "x")
+    w = _req(w, torch.float32, "weight")
+    return gemm(x, x.size(1), 1, w, w.size(1), 1, x.size(0), w.size(0), x.size(1), precision=precision)
+
+
+def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False):
+    rowptr, _perm, nbr = csr
+    n, d = h.shape
+    if out is None:
+        out = torch.empty(n, d, dtype=torch.float32, device=h.device)
+    flags = (SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0)
+    check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(norm.dis) if norm is not None else None,
+                         _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
+                         float(p_drop), int(seed), _stream()), "sgs_spmm")
+    return out
+
+
+class GCNConvFn(torch.autograd.Function):
+    """GCNConv (PyG 2.3.1 semantics) with optional fused ReLU + dropout epilogue:
+        out = dropout(relu(A_hat (x W^T) + b)).
+    Backward: SpMM over the by-source CSR, SDDMM-based edge-weight gradient (A.3), dense dW/dx."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, edge_weight, graph, relu, p_drop, seed):
+        x = _req(x, torch.float32, "x")
+        weight = _req(weight, torch.float32, "weight")
+        bias = _req(bias, torch.float32, "bias")
+        if x.size(0) != graph.num_nodes:
+            raise RuntimeError("x must have one row per node")
+        norm = graph.norm(edge_weight)
+        h = linear_nt(x, weight)
+        out = spmm(graph.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed)
+        ctx.graph, ctx.norm, ctx.relu, ctx.p_drop = graph, norm, relu, p_drop
+        ctx.has_w = edge_weight is not None
+        ctx.save_for_backward(x, weight, h if ctx.has_w else None, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight, h, out = ctx.saved_tensors
+        graph, norm = ctx.graph, ctx.norm
+        n, d = gout.shape
+        gout = _req(gout, torch.float32, "grad")
+        if ctx.relu:
+            g = torch.empty_like(gout)
+            scale = 1.0 / (1.0 - ctx.p_drop) if ctx.p_drop > 0 else 1.0
+            check(lib().sgs_act_bwd(_p(gout), _p(out), gout.numel(), scale, _p(g), _stream()), "sgs_act_bwd")
+        else:
+            g = gout
+        need_x, need_w, need_b, need_ew = ctx.needs_input_grad[:4]
+        db = dw = dx = dew = None
+        if need_b:
+            db = torch.empty(d, dtype=torch.float32, device=g.device)
+            check(lib().sgs_colsum(_p(g), n, d, _p(db), _stream()), "sgs_colsum")
+        if need_w or need_x:
+            dh = spmm(graph.csr_src, norm.what_src, norm, g)
+            fin = x.size(1)
+            if need_w:  # dW[d, fin] = dh^T x
+                dw = gemm(dh, 1, d, x, 1, fin, d, fin, n)
+            if need_x:  # dx[n, fin] = dh W
+                dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d)
+        if need_ew and ctx.has_w:
+            m = graph.num_edges
+            dew = torch.empty(m, dtype=torch.float32, device=g.device)
+            tmp = torch.empty(2 * m + n, dtype=torch.float32, device=g.device)
+            rp_d, pm_d, nb_d = graph.csr_dst
+            rp_s, pm_s, _ = graph.csr_src
+            check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(rp_s), _p(pm_s),
+                                          _p(graph.src), _p(graph.dst), _p(g), _p(h), _p(norm.dis), _p(norm.deg),
+                                          _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]), _p(tmp[2 * m:]), _p(dew),
+                                          0, _stream()), "sgs_gcn_edge_grad")
+        return dx, dw, db, dew, None, None, None, None
+
+
+def gcn_conv(x, weight, bias, graph, edge_weight=None, relu=False, p_drop=0.0, seed=0):
+    return GCNConvFn.apply(x, weight, bias, edge_weight, graph, relu, float(p_drop), int(seed))
+
+
+# ------------------------------------------------------------------------------------------
+# edge scorer
+# ------------------------------------------------------------------------------------------
+
+def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0, precision=None):
+    """p[n] for edges `ids` (int32) or all edges of `graph` (no autograd)."""
+    prec = _state["scorer"] if precision is None else precision
+    out = _req(out, torch.float32, "out")
+    n_nodes, h = out.shape
+    n = graph.num_edges if ids is None else int(ids.numel())
+    p = torch.empty(n, dtype=torch.float32, device=out.device)
+    nbytes = lib().sgs_edge_score_workspace_bytes(n, h, prec, 0)
+    ws = _ws(nbytes, out.device)
+    check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1), _p(b1),
+                                   _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(ws), ws.numel(), prec,
+                                   _stream()), "sgs_edge_score_fwd")
+    return p
+
+
+class EdgeScoreFn(torch.autograd.Function):
+    """_edge_score (model.py:115-122) over all edges or an id subset.  `precomputed` lets the
+    hybrid pipeline reuse the no-grad full-graph probabilities for the forward value while the
+    backward still runs (recompute + gradient) over just these edges."""
+
+    @staticmethod
+    def forward(ctx, out, w1, b1, w2, b2, graph, ids, p_drop, seed, precomputed, precision):
+        w1 = _req(w1, torch.float32, "fc1.weight")
+        b1 = _req(b1, torch.float32, "fc1.bias")
+        w2 = _req(w2.reshape(-1), torch.float32, "fc2.weight")
+        b2 = _req(b2.reshape(-1), torch.float32, "fc2.bias")
+        out = _req(out, torch.float32, "out")
+        if precomputed is None:
+            p = edge_score_forward(out, graph, w1, b1, w2, b2, ids, p_drop, seed, precision)
+        else:
+            p = precomputed
+        ctx.graph, ctx.ids, ctx.p_drop, ctx.seed = graph, ids, p_drop, seed
+        ctx.save_for_backward(out, w1, b1, w2, b2)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        out, w1, b1, w2, b2 = ctx.saved_tensors
+        graph, ids = ctx.graph, ctx.ids
+        dp = _req(dp, torch.float32, "grad")
+        n_nodes, h = out.shape
+        n = dp.numel()
+        dev = out.device
+        d_out = torch.zeros_like(out)
+        dw1 = torch.zeros_like(w1)
+        small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
+        nbytes = lib().sgs_edge_score_workspace_bytes(n, h, PREC_FP32, 1)
+        ws = _ws(nbytes, dev)
+        check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1), _p(b1),
+                                       _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(dp), _p(d_out), _p(dw1),
+                                       _p(small), _p(small[h:]), _p(small[2 * h:]), _p(ws), ws.numel(),
+                                       _state["scorer"], _stream()), "sgs_edge_score_bwd")
+        db1, dw2, db2 = small[:h], small[h:2 * h], small[2 * h:]
+        return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None
+
+
+def edge_score(out, w1, b1, w2, b2, graph, ids=None, p_drop=0.0, seed=0, precomputed=None, precision=None):
+    return EdgeScoreFn.apply(out, w1, b1, w2, b2, graph, ids, float(p_drop), int(seed), precomputed, precision)
+
+
+# ------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------
+
+def sum_f32(p):
+    p = _req(p, torch.float32, "p")
+    s = torch.empty(1, dtype=torch.float32, device=p.device)
+    ws = _ws(8192, p.device)
+    check(lib().sgs_sum_f32(_p(p), p.numel(), _p(s), _p(ws), ws.numel(), _stream()), "sgs_sum_f32")
+    return s
+
+
+def softmax_f32(x):
+    x = _req(x, torch.float32, "x")
+    out = torch.empty_like(x)
+    ws = _ws(16384, x.device)
+    check(lib().sgs_softmax_f32(_p(x), x.numel(), _p(out), _p(ws), ws.numel(), _stream()), "sgs_softmax_f32")
+    return out
+
+
+def exponential(n, device, seed=None):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(lib().sgs_exponential_f32(_p(out), n, next_seed() if seed is None else int(seed), _stream()),
+          "sgs_exponential_f32")
+    return out
+
+
+def _coefs(coef):
+    # exactly as Python evaluates sampling.py:95: (1 - coef) in double, then each scalar -> fp32
+    return float(np.float32(1.0 - float(coef))), float(np.float32(float(coef)))
+
+
+class TopQ:
+    """Result of one draw: sel (int32 [q], ascending edge ids), optional mask (uint8 [E]) and the
+    device state vector (tau bits, counts, invalid-input flag)."""
+    __slots__ = ("sel", "mask", "state", "S", "mode", "coef", "q", "E")
+
+    def check_valid(self):
+        st = self.state.cpu()
+        if int(st[5]) != 0:
+            raise RuntimeError("probability tensor contains either `inf`, `nan` or element < 0")
+        if int(st[7]) != self.q:
+            raise RuntimeError(f"sampler selected {int(st[7])} edges, expected {self.q}")
+        return st
+
+    @property
+    def tau(self):
+        bits = int(self.state[2].item()) & 0xFFFFFFFF
+        return float(np.array([bits], dtype=np.uint32).view(np.float32)[0])
+
+
+def sample_topq(p, prob, q, mode=SAMPLE_TRAIN, coef=0.3, noise=None, S=None, want_mask=False, seed=None,
+                validate=True):
+    """Top-q of key = s/noise (include/sgs_b200.h K2).  noise: injected Exp(1) tensor, or None to
+    draw it on device.  S: injected normaliser (device float tensor [1]) or None to reduce p."""
+    p = _req(p, torch.float32, "edge_probs")
+    e = p.numel()
+    q = int(q)
+    if q > e:
+        raise RuntimeError("cannot sample n_sample > prob_dist.size(-1) samples without replacement")
+    if q < 1:
+        raise RuntimeError("cannot sample n_sample <= 0 samples")
+    dev = p.device
+    if mode == SAMPLE_TRAIN:
+        prob = _req(prob, torch.float32, "batch.prob")
+        if prob.numel() != e:
+            raise RuntimeError(f"batch.prob has {prob.numel()} entries but edge_probs has {e}")
+    else:
+        prob = None
+    if noise is None:
+        noise = exponential(e, dev, seed)
+    else:
+        noise = _req(noise, torch.float32, "noise")
+        if noise.numel() != e:
+            raise RuntimeError("noise must have one entry per edge")
+    if mode != SAMPLE_RAW and S is None:
+        S = sum_f32(p)
+    one_m, c = _coefs(coef)
+    keys = torch.empty(e, dtype=torch.int32, device=dev)
+    sel = torch.empty(q, dtype=torch.int32, device=dev)
+    mask = torch.empty(e, dtype=torch.uint8, device=dev) if want_mask else None
+    state = torch.empty(8, dtype=torch.int64, device=dev)
+    nbytes = lib().sgs_topq_workspace_bytes(e) + _lib.TOPQ_BINS * 8
+    ws = _ws(nbytes, dev)
+    check(lib().sgs_sample_topq(_p(p), _p(prob), _p(noise), e, q, one_m, c, mode, _p(S), _p(keys), _p(sel), _p(mask),
+                                _p(state), _p(ws), ws.numel(), _stream()), "sgs_sample_topq")
+    r = TopQ()
+    r.sel, r.mask, r.state, r.S, r.mode, r.coef, r.q, r.E = sel, mask, state, S, mode, coef, q, e
+    if validate:
+        r.check_valid()
+    return r
+
+
+def gather_selected(p, prob, sel, mode, coef, S, straight_through=False):
+    q = sel.numel()
+    one_m, c = _coefs(coef)
+    p_sel = torch.empty(q, dtype=torch.float32, device=p.device)
+    w_st = torch.empty_like(p_sel) if straight_through else None
+    check(lib().sgs_gather_selected(_p(p), _p(prob), _p(sel), q, one_m, c, mode, _p(S), _p(p_sel), _p(w_st),
+                                    _stream()), "sgs_gather_selected")
+    return p_sel, w_st
+
+
+class GatherSelectedFn(torch.autograd.Function):
+    """p_full[mask] (training_hybrid.py:86): gather forward, scatter into zeros[E] backward."""
+
+    @staticmethod
+    def forward(ctx, p_full, sel):
+        p_full = _req(p_full, torch.float32, "edge_probs")
+        ctx.sel, ctx.e = sel, p_full.numel()
+        return gather_selected(p_full, None, sel, SAMPLE_RAW, 0.0, None)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _req(g, torch.float32, "grad")
+        out = torch.zeros(ctx.e, dtype=torch.float32, device=g.device)
+        check(lib().sgs_scatter_selected(_p(g), _p(ctx.sel), g.numel(), _p(out), _stream()), "sgs_scatter_selected")
+        return out, None
+
+
+class StraightThroughWeightsFn(torch.autograd.Function):
+    """(p * st)[mask].clamp(0,1) with st = (one_hot - s).detach() + s (sampling.py:137-155) and the
+    dense backward of SURVEY A.4:
+        dL/dp_j = gamma_j (st_j + a p_j / S') - (a / S'^2) sum_i gamma_i p_i^2."""
+
+    @staticmethod
+    def forward(ctx, p_full, prob, sel, S, mode, coef):
+        p_full = _req(p_full, torch.float32, "edge_probs")
+        p_sel, w = gather_selected(p_full, prob, sel, mode, coef, S, straight_through=True)
+        ctx.sel, ctx.mode, ctx.coef, ctx.e = sel, mode, coef, p_full.numel()
+        ctx.save_for_backward(p_sel, w, S)
+        return w
+
+    @staticmethod
+    def backward(ctx, g):
+        p_sel, w, S = ctx.saved_tensors
+        a = float(np.float32(1.0 - ctx.coef)) if ctx.mode == SAMPLE_TRAIN else 1.0
+        s_eff = S + 1e-12
+        gamma = torch.where((w > 0) & (w < 1), g, torch.zeros_like(g))
+        const = (a / (s_eff * s_eff)) * (gamma * p_sel * p_sel).sum()
+        sel_term = gamma * (1.0 + a * p_sel / s_eff)
+        out = (-const).expand(ctx.e).contiguous()
+        check(lib().sgs_scatter_selected(_p(sel_term.contiguous()), _p(ctx.sel), sel_term.numel(), _p(out),
+                                         _stream()), "sgs_scatter_selected")
+        return out, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------
+
+class LossStats:
+    """Device accumulator of sgs_loss_fwd: {ce_sum, n_train, correct, bce_sum, n_valid, sum_label,
+    mse_sum, q} as float64[8]."""
+    __slots__ = ("acc",)
+
+
+def loss_forward(logits, y, train_mask_u8, sub=None, p_s=None):
+    logits = _req(logits, torch.float32, "logits")
+    n, c = logits.shape
+    acc = torch.empty(8, dtype=torch.float64, device=logits.device)
+    with_edges = sub is not None
+    q = sub.num_edges if with_edges else 0
+    check(lib().sgs_loss_fwd(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(sub.src) if with_edges else None,
+                             _p(sub.dst) if with_edges else None, _p(p_s) if with_edges else None, q,
+                             1 if with_edges else 0, _p(acc), _stream()), "sgs_loss_fwd")
+    return acc
+
+
+class FusedLossFn(torch.autograd.Function):
+    """CE(logits[train], y[train]) [+ c1*BCE_reg1 + c2*MSE_reg2 over the sampled edges]
+    (training_hybrid.py:103-132).  `acc` may be a precomputed sgs_loss_fwd accumulator."""
+
+    @staticmethod
+    def forward(ctx, logits, p_s, y, train_mask_u8, sub, c0, c1, c2, reg1, reg2, acc):
+        logits = _req(logits, torch.float32, "logits")
+        with_edges = sub is not None and p_s is not None and (reg1 or reg2)
+        if with_edges:
+            p_s = _req(p_s, torch.float32, "edge_probs")
+        if acc is None:
+            acc = loss_forward(logits, y, train_mask_u8, sub if with_edges else None, p_s if with_edges else None)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        check(lib().sgs_loss_finish(_p(acc), c0, c1, c2, 1 if (reg1 and with_edges) else 0,
+                                    1 if (reg2 and with_edges) else 0, _p(loss), _stream()), "sgs_loss_finish")
+        ctx.sub, ctx.c0, ctx.c1, ctx.c2, ctx.reg1, ctx.reg2, ctx.with_edges = sub, c0, c1, c2, reg1, reg2, with_edges
+        ctx.save_for_backward(logits, p_s if with_edges else None, y, train_mask_u8, acc)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, p_s, y, tm, acc = ctx.saved_tensors
+        n, c = logits.shape
+        sub = ctx.sub
+        g = g.reshape(1).to(torch.float32).contiguous()
+        dlogits = torch.empty_like(logits)
+        dp = torch.empty_like(p_s) if ctx.with_edges else None
+        q = sub.num_edges if ctx.with_edges else 0
+        check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(sub.src) if ctx.with_edges else None,
+                                 _p(sub.dst) if ctx.with_edges else None, _p(p_s), q, 1 if ctx.with_edges else 0,
+                                 _p(acc), ctx.c0, ctx.c1, ctx.c2, 1 if ctx.reg1 else 0, 1 if ctx.reg2 else 0, _p(g),
+                                 _p(dlogits), _p(dp), _stream()), "sgs_loss_bwd")
+        return dlogits, dp, None, None, None, None, None, None, None, None, None
+
+
+def fused_loss(logits, y, train_mask_u8, p_s=None, sub=None, c1=1.0, c2=0.5, reg1=True, reg2=True, acc=None,
+               c0=1.0):
+    return FusedLossFn.apply(logits, p_s, y, train_mask_u8, sub, float(c0), float(c1), float(c2), bool(reg1),
+                             bool(reg2), acc)

@@ -1,0 +1,129 @@
+"""GPU parity: K3 (gcn_norm, SpMM fwd/bwd, edge-weight gradient) and K4 (dense contraction) through
+the C ABI vs the CPU oracle.  Tolerance: 1e-4 relative (north_star), measured against max-norm."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import extended as ox
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 64, 16), (300, 41, 256), (1000, 256, 602), (7, 5, 3), (256, 512, 5000)])
+def test_gemm_forms(dev, m, n, k):
+    from sgs_gnn_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    want = (a.double() @ b.double().t()).float()
+    ad, bd = a.to(dev), b.to(dev)
+    assert relerr(ops.linear_nt(ad, bd).cpu(), want) < 1e-5
+    # TN: C = A^T B with A [k,m], B [k,n]
+    at, bt = a.t().contiguous().to(dev), b.t().contiguous().to(dev)
+    c = ops.gemm(at, 1, m, bt, 1, n, m, n, k)
+    assert relerr(c.cpu(), want) < 1e-5
+    # NN with accumulate
+    c0 = torch.ones(m, n, device=dev)
+    c = ops.gemm(ad, k, 1, bt, 1, n, m, n, k, out=c0, accumulate=True)
+    assert relerr(c.cpu(), want + 1.0) < 1e-5
+
+
+def _rand_graph(n, m, seed, self_loops=False):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, m), generator=g)
+    if not self_loops:
+        ei[1] = torch.where(ei[0] == ei[1], (ei[1] + 1) % n, ei[1])
+    return ei
+
+
+@pytest.mark.parametrize("d", [41, 256, 64, 7])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_gcn_conv_forward_backward(dev, d, weighted):
+    from sgs_gnn_b200 import ops
+    n, m, f = 500, 6000, 48
+    ei = _rand_graph(n, m, d + weighted, self_loops=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, f, generator=g)
+    W = torch.randn(d, f, generator=g) * 0.2
+    b = torch.randn(d, generator=g) * 0.1
+    w = torch.rand(m, generator=g) if weighted else None
+    G = torch.randn(n, d, generator=g)
+
+    xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True) if weighted else None
+    out_ref = torch.relu(ox.gcn_conv(xr, Wr, br, ei, wr))
+    grads_ref = torch.autograd.grad((out_ref * G).sum(), [xr, Wr, br] + ([wr] if weighted else []))
+
+    xd, Wd, bd = (v.to(dev).requires_grad_(True) for v in (x, W, b))
+    wd = w.to(dev).requires_grad_(True) if weighted else None
+    graph = ops.graph_of(ei.to(dev), n)
+    out = ops.gcn_conv(xd, Wd, bd, graph, wd, relu=True)
+    assert relerr(out.detach().cpu(), out_ref.detach()) < RTOL
+    grads = torch.autograd.grad((out * G.to(dev)).sum(), [xd, Wd, bd] + ([wd] if weighted else []))
+    for name, a, r in zip(("dx", "dW", "db", "dw"), grads, grads_ref):
+        if name == "dw":  # input self-loop edges: gradient not propagated (documented)
+            keep = ei[0] != ei[1]
+            assert relerr(a.cpu()[keep], r[keep]) < RTOL, name
+        else:
+            assert relerr(a.cpu(), r) < RTOL, name
+
+
+def test_gcn_norm_edge_cases(dev):
+    from sgs_gnn_b200 import ops
+    # isolated nodes, duplicate edges, an input self loop carrying a weight
+    n = 6
+    ei = torch.tensor([[0, 0, 1, 2, 2, 4], [1, 1, 0, 2, 3, 3]])
+    w = torch.tensor([0.5, 0.25, 1.0, 0.3, 0.7, 0.9])
+    row2, col2, w_hat, deg, dis, loop_w = ox.gcn_norm(ei, w, n)
+    graph = ops.graph_of(ei.to(dev), n)
+    nrm = graph.norm(w.to(dev))
+    assert torch.allclose(nrm.deg.cpu(), deg, rtol=1e-6) and torch.allclose(nrm.dis.cpu(), dis, rtol=1e-6)
+    assert torch.allclose(nrm.loopw.cpu(), loop_w)
+    x = torch.eye(n)
+    out = ops.gcn_conv(x.to(dev), torch.eye(n, device=dev), torch.zeros(n, device=dev), graph, w.to(dev))
+    want = ox.gcn_conv(x, torch.eye(n), torch.zeros(n), ei, w)
+    assert torch.allclose(out.cpu(), want, atol=1e-6)
+    # empty edge set: out = x W^T + b
+    e0 = torch.zeros(2, 0, dtype=torch.int64, device=dev)
+    out = ops.gcn_conv(x.to(dev), torch.eye(n, device=dev), torch.ones(n, device=dev), ops.graph_of(e0, n), None)
+    assert torch.allclose(out.cpu(), x + 1.0)
+
+
+def test_fused_dropout_matches_host_mirror(dev):
+    from sgs_gnn_b200 import ops, rng
+    n, m, f, d = 300, 2000, 16, 64
+    ei = _rand_graph(n, m, 1)
+    g = torch.Generator().manual_seed(2)
+    x, W, b = torch.randn(n, f, generator=g), torch.randn(d, f, generator=g), torch.zeros(d)
+    graph = ops.graph_of(ei.to(dev), n)
+    seed, p = 424242, 0.3
+    out = ops.gcn_conv(x.to(dev), W.to(dev), b.to(dev), graph, None, relu=True, p_drop=p, seed=seed).cpu()
+    keep = torch.from_numpy(rng.keep_mask(seed, np.arange(n), d, p))
+    want = torch.relu(ox.gcn_conv(x, W, b, ei)) * keep / (1 - p)
+    assert relerr(out, want) < RTOL
+    assert abs(float(keep.float().mean()) - 0.7) < 0.02
+
+
+def test_golden_gnn_forward(dev):
+    from sgs_gnn_b200.model import GNNModel
+    z = load_golden("forward_small.npz")
+    sd = {k[3:]: t(v) for k, v in z.items() if k.startswith("sd.")}
+    model = GNNModel(24, 32, 5, 0.3, "GCN")
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+
+    class D:
+        x = t(z["x"], dev)
+
+    rei = t(z["rand_edge_index"], dev)
+    with torch.no_grad():
+        lw = model(D, rei, t(z["w"], dev))
+        lu = model(D, rei)
+    assert relerr(lw.cpu(), t(z["logits_weighted"])) < RTOL
+    assert relerr(lu.cpu(), t(z["logits_unweighted"])) < RTOL

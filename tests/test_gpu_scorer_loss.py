@@ -1,0 +1,101 @@
+"""GPU parity: K1/K1b edge scorer and K5 fused losses through the C ABI vs oracle + golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import extended as ox
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def test_golden_scorer_probabilities(dev):
+    from sgs_gnn_b200.model import GNNModel
+    z = load_golden("forward_small.npz")
+    sd = {k[3:]: t(v) for k, v in z.items() if k.startswith("sd.")}
+    model = GNNModel(24, 32, 5, 0.3, "GCN")
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    x, ei, rei = t(z["x"], dev), t(z["edge_index"], dev), t(z["rand_edge_index"], dev)
+    with torch.no_grad():
+        ps = model.edge_prob_mlp(x, ei, rei)
+        pf = model.edge_prob_mlp(x, ei, None, use_checkpoint=True)
+    assert ps.shape == (ei.size(1), 1)
+    assert relerr(ps.squeeze().cpu(), t(z["p_sparse"])) < RTOL
+    assert relerr(pf.squeeze().cpu(), t(z["p_fullgraph"])) < RTOL
+
+
+@pytest.mark.parametrize("h,p_drop,subset", [(32, 0.0, False), (256, 0.0, True), (64, 0.3, False), (128, 0.3, True)])
+def test_scorer_forward_backward_vs_oracle(dev, h, p_drop, subset):
+    from sgs_gnn_b200 import ops, rng
+    n, e = 300, 4000
+    g = torch.Generator().manual_seed(h)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    out = torch.relu(torch.randn(n, h, generator=g))
+    W1 = (torch.rand(h, 2 * h, generator=g) - 0.5) * (2 / (2 * h) ** 0.5)
+    b1 = (torch.rand(h, generator=g) - 0.5) * 0.1
+    w2 = (torch.rand(1, h, generator=g) - 0.5) * (2 / h ** 0.5)
+    b2 = torch.tensor([0.05])
+    ids = torch.sort(torch.randperm(e, generator=g)[:900]).values if subset else torch.arange(e)
+    seed = 99
+    keep = torch.from_numpy(rng.keep_mask(seed, ids.numpy(), h, p_drop)) if p_drop > 0 else None
+    gup = torch.randn(ids.numel(), generator=g)
+
+    ro, rW1, rb1, rw2, rb2 = (v.clone().requires_grad_(True) for v in (out, W1, b1, w2, b2))
+    p_ref = ox.edge_score(ro, ei[:, ids], rW1, rb1, rw2, rb2, p_drop, keep, True).squeeze(-1)
+    g_ref = torch.autograd.grad((p_ref * gup).sum(), [ro, rW1, rb1, rw2, rb2])
+
+    graph = ops.graph_of(ei.to(dev), n)
+    do, dW1, db1, dw2, db2 = (v.to(dev).requires_grad_(True) for v in (out, W1, b1, w2, b2))
+    ids_d = ids.to(dev).int() if subset else None
+    p = ops.edge_score(do, dW1, db1, dw2, db2, graph, ids_d, p_drop, seed)
+    assert relerr(p.detach().cpu(), p_ref.detach()) < RTOL
+    grads = torch.autograd.grad((p * gup.to(dev)).sum(), [do, dW1, db1, dw2, db2])
+    for name, a, r in zip(("d_out", "dW1", "db1", "dw2", "db2"), grads, g_ref):
+        assert relerr(a.cpu().reshape(r.shape), r) < RTOL, name
+
+
+def test_golden_losses_and_grads(dev):
+    from sgs_gnn_b200 import ops, utils
+    z = load_golden("losses_small.npz")
+    logits = t(z["logits"], dev).requires_grad_(True)
+    p_s = t(z["p_s"], dev).requires_grad_(True)
+    s_ei, y, tm = t(z["s_ei"], dev), t(z["y"], dev), t(z["train_mask"], dev)
+    sub = ops.graph_of(s_ei, logits.size(0))
+    loss = ops.fused_loss(logits, y, tm.view(torch.uint8), p_s, sub, 1.0, 0.5, True, True)
+    assert abs(loss.item() - float(z["total"])) < 1e-5 * abs(float(z["total"]))
+    gl, gp = torch.autograd.grad(loss, [logits, p_s])
+    assert relerr(gl.cpu(), t(z["grad_logits"])) < RTOL
+    assert relerr(gp.cpu(), t(z["grad_p"])) < RTOL
+    acc = ops.loss_forward(logits.detach(), y, tm.view(torch.uint8), sub, p_s.detach()).cpu()
+    assert int(acc[4]) == int(z["n_valid"]) and float(acc[5]) == float(z["sum_label"])
+    assert abs(float(acc[0] / acc[1]) - float(z["ce"])) < 1e-5
+    assert abs(float(acc[3] / acc[4]) - float(z["bce"])) < 1e-5
+    assert abs(float(acc[6] / acc[7]) - float(z["cons"])) < 1e-5
+    assert abs(utils.calculate_f1(logits.detach(), y, tm) - float(z["f1"])) < 1e-9
+    # stand-alone consistency_loss (utils.py:187-211) with gradients to both arguments
+    l2 = utils.consistency_loss(p_s, s_ei, logits)
+    assert abs(l2.item() - float(z["cons"])) < 1e-6
+    ref_l = t(z["logits"]).requires_grad_(True)
+    ref_p = t(z["p_s"]).requires_grad_(True)
+    rg = torch.autograd.grad(ox.consistency_loss(ref_p, t(z["s_ei"]), ref_l), [ref_l, ref_p])
+    og = torch.autograd.grad(l2, [logits, p_s])
+    assert relerr(og[0].cpu(), rg[0]) < RTOL and relerr(og[1].cpu(), rg[1]) < RTOL
+
+
+def test_reg1_skipped_when_at_most_one_positive_label(dev):
+    from sgs_gnn_b200 import ops
+    n, c = 10, 3
+    logits = torch.randn(n, c, device=dev, requires_grad=True)
+    y = torch.arange(n, device=dev) % c
+    tm = torch.ones(n, dtype=torch.bool, device=dev)
+    s_ei = torch.tensor([[0, 1, 2], [3, 5, 4]], device=dev)     # labels: same(0,3), diff, diff -> sum = 1
+    p_s = torch.tensor([0.3, 0.6, 0.8], device=dev, requires_grad=True)
+    loss = ops.fused_loss(logits, y, tm.view(torch.uint8), p_s, ops.graph_of(s_ei, n), 1.0, 0.5, True, True)
+    want = ox.hybrid_loss(logits.detach().cpu(), p_s.detach().cpu(), s_ei.cpu(), y.cpu(), tm.cpu())
+    assert abs(loss.item() - float(want)) < 1e-5
