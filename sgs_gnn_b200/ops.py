@@ -76,6 +76,48 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+# optional per-kernel-family CUDA-event timing (bench.py's roofline leg); off by default
+_timer = None
+
+
+class KernelTimer:
+    """Collects (start, end) CUDA events on the launching stream around each wrapped C-ABI call."""
+
+    def __init__(self):
+        self.events = {}
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+
+class _timed:
+    __slots__ = ("name", "a")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _timer is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _timer.events.setdefault(self.name, []).append((self.a, b))
+
+
 # ------------------------------------------------------------------------------------------
 # graph structure
 # ------------------------------------------------------------------------------------------
@@ -165,8 +207,9 @@ class Graph:
         nbr = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
         nbytes = lib().sgs_csr_workspace_bytes(m, n)
         ws = _ws(nbytes, self.device)
-        check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(ws), ws.numel(),
-                                  _stream()), "sgs_csr_build")
+        with _timed("csr_build"):
+            check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(ws), ws.numel(),
+                                      _stream()), "sgs_csr_build")
         return rowptr, perm, nbr
 
     @property
@@ -228,8 +271,9 @@ def gemm(a, a_sm, a_sk, b, b_sn, b_sk, m, n, k, out=None, accumulate=False, prec
     prec = _state["gemm"] if precision is None else precision
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device=a.device)
-    check(lib().sgs_gemm(_p(a), a_sm, a_sk, _p(b), b_sn, b_sk, _p(out), out.stride(0), m, n, k,
-                         1 if accumulate else 0, prec, _stream()), "sgs_gemm")
+    with _timed("gemm"):
+        check(lib().sgs_gemm(_p(a), a_sm, a_sk, _p(b), b_sn, b_sk, _p(out), out.stride(0), m, n, k,
+                             1 if accumulate else 0, prec, _stream()), "sgs_gemm")
     return out
 
 
@@ -246,9 +290,10 @@ def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None
     if out is None:
         out = torch.empty(n, d, dtype=torch.float32, device=h.device)
     flags = (SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0)
-    check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(norm.dis) if norm is not None else None,
-                         _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
-                         float(p_drop), int(seed), _stream()), "sgs_spmm")
+    with _timed(f"spmm_d{d}"):
+        check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(norm.dis) if norm is not None else None,
+                             _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
+                             float(p_drop), int(seed), _stream()), "sgs_spmm")
     return out
 
 
@@ -302,10 +347,11 @@ class GCNConvFn(torch.autograd.Function):
             tmp = torch.empty(2 * m + n, dtype=torch.float32, device=g.device)
             rp_d, pm_d, nb_d = graph.csr_dst
             rp_s, pm_s, _ = graph.csr_src
-            check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(rp_s), _p(pm_s),
-                                          _p(graph.src), _p(graph.dst), _p(g), _p(h), _p(norm.dis), _p(norm.deg),
-                                          _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]), _p(tmp[2 * m:]), _p(dew),
-                                          0, _stream()), "sgs_gcn_edge_grad")
+            with _timed(f"edge_grad_d{d}"):
+                check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(rp_s), _p(pm_s),
+                                              _p(graph.src), _p(graph.dst), _p(g), _p(h), _p(norm.dis),
+                                              _p(norm.deg), _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]),
+                                              _p(tmp[2 * m:]), _p(dew), 0, _stream()), "sgs_gcn_edge_grad")
         return dx, dw, db, dew, None, None, None, None
 
 
@@ -326,9 +372,10 @@ def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0,
     p = torch.empty(n, dtype=torch.float32, device=out.device)
     nbytes = lib().sgs_edge_score_workspace_bytes(n, h, prec, 0)
     ws = _ws(nbytes, out.device)
-    check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1), _p(b1),
-                                   _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(ws), ws.numel(), prec,
-                                   _stream()), "sgs_edge_score_fwd")
+    with _timed("edge_score_fwd"):
+        check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
+                                       _p(b1), _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(ws), ws.numel(),
+                                       prec, _stream()), "sgs_edge_score_fwd")
     return p
 
 
@@ -339,6 +386,7 @@ class EdgeScoreFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, out, w1, b1, w2, b2, graph, ids, p_drop, seed, precomputed, precision):
+        ctx.w2_shape, ctx.b2_shape = w2.shape, b2.shape
         w1 = _req(w1, torch.float32, "fc1.weight")
         b1 = _req(b1, torch.float32, "fc1.bias")
         w2 = _req(w2.reshape(-1), torch.float32, "fc2.weight")
@@ -365,11 +413,12 @@ class EdgeScoreFn(torch.autograd.Function):
         small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
         nbytes = lib().sgs_edge_score_workspace_bytes(n, h, PREC_FP32, 1)
         ws = _ws(nbytes, dev)
-        check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1), _p(b1),
-                                       _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(dp), _p(d_out), _p(dw1),
-                                       _p(small), _p(small[h:]), _p(small[2 * h:]), _p(ws), ws.numel(),
-                                       _state["scorer"], _stream()), "sgs_edge_score_bwd")
-        db1, dw2, db2 = small[:h], small[h:2 * h], small[2 * h:]
+        with _timed("edge_score_bwd"):
+            check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
+                                           _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(dp),
+                                           _p(d_out), _p(dw1), _p(small), _p(small[h:]), _p(small[2 * h:]), _p(ws),
+                                           ws.numel(), _state["scorer"], _stream()), "sgs_edge_score_bwd")
+        db1, dw2, db2 = small[:h], small[h:2 * h].reshape(ctx.w2_shape), small[2 * h:].reshape(ctx.b2_shape)
         return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None
 
 
@@ -461,8 +510,9 @@ def sample_topq(p, prob, q, mode=SAMPLE_TRAIN, coef=0.3, noise=None, S=None, wan
     state = torch.empty(8, dtype=torch.int64, device=dev)
     nbytes = lib().sgs_topq_workspace_bytes(e) + _lib.TOPQ_BINS * 8
     ws = _ws(nbytes, dev)
-    check(lib().sgs_sample_topq(_p(p), _p(prob), _p(noise), e, q, one_m, c, mode, _p(S), _p(keys), _p(sel), _p(mask),
-                                _p(state), _p(ws), ws.numel(), _stream()), "sgs_sample_topq")
+    with _timed("sample_topq"):
+        check(lib().sgs_sample_topq(_p(p), _p(prob), _p(noise), e, q, one_m, c, mode, _p(S), _p(keys), _p(sel),
+                                    _p(mask), _p(state), _p(ws), ws.numel(), _stream()), "sgs_sample_topq")
     r = TopQ()
     r.sel, r.mask, r.state, r.S, r.mode, r.coef, r.q, r.E = sel, mask, state, S, mode, coef, q, e
     if validate:
@@ -574,7 +624,8 @@ class FusedLossFn(torch.autograd.Function):
         dlogits = torch.empty_like(logits)
         dp = torch.empty_like(p_s) if ctx.with_edges else None
         q = sub.num_edges if ctx.with_edges else 0
-        check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(sub.src) if ctx.with_edges else None,
+        with _timed("loss_bwd"):
+          check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(sub.src) if ctx.with_edges else None,
                                  _p(sub.dst) if ctx.with_edges else None, _p(p_s), q, 1 if ctx.with_edges else 0,
                                  _p(acc), ctx.c0, ctx.c1, ctx.c2, 1 if ctx.reg1 else 0, 1 if ctx.reg2 else 0, _p(g),
                                  _p(dlogits), _p(dp), _stream()), "sgs_loss_bwd")
