@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- Reddit-shape hybrid-pipeline training epochs on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload reddit] [--precision bf16]
+
+A "step" is one epoch = one call of training_hybrid.train over a one-batch loader holding the
+whole synthetic graph (one learned-sparsifier step: baseline draw, edge scoring of all E edges,
+top-q sampling, two GNN forwards, conditional gate, fused losses, backward, Adam).
+metric = sampled edges per second = q * K / t.
+
+  value  : graph resident in HBM before the timed region (loader holds the CUDA batch)
+  e2e    : same call with the batch in pinned HOST memory; train() uploads it every step
+           (batch.to(device), as the reference does at training_hybrid.py:42) and reads the
+           gate counters + loss back -- H2D/D2H inside the timed region
+  roofline: the dominant kernel (edge scorer forward over all E edges) timed live with CUDA
+           events on the launching stream inside the timed region
+  cpu_baseline / --impl reference: the CPU oracle (the reference's algorithm, oracle/extended.py;
+           the reference itself needs PyTorch-Geometric, absent from this image) on a bounded,
+           proportionally shrunk sample of the same workload on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN = 256
+SAMPLE_PERC = 0.2
+
+
+def make_args(device, drop_rate=0.3):
+    from types import SimpleNamespace
+    return SimpleNamespace(device=device, mode="learned", hybrid_checkpoint=False, conditional=True,
+                           sparse_edge_mlp=True, t_init=0.7, t_min=0.5, degree_bias_coef=0.3, reg1=True, reg2=True,
+                           regularizer1_coef=1.0, consist_reg_coef=0.5, pipeline="hybrid", drop_rate=drop_rate)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.path or not os.path.isfile(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def build_model(f, c, device, drop_rate):
+    from sgs_gnn_b200.model import GNNModel
+    torch.manual_seed(42)
+    model = GNNModel(f, HIDDEN, c, drop_rate, "GCN").to(device)
+    og = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-3)
+    oe = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-3)
+    oa = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    return model, og, oe, oa
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------
+
+def cpu_epochs(workload, scale, steps, warmup, drop_rate=0.3):
+    from oracle import extended as ox
+    from sgs_gnn_b200 import synth
+    torch.manual_seed(42)
+    n0, e0 = synth.SHAPES[workload][:2]
+    e_s = max(8, round(e0 * scale))
+    # keep the sample a simple graph: N shrinks with E but never below ~8*sqrt(E)
+    n_s = max(round(n0 * scale), int(8 * e_s ** 0.5) + 1)
+    b = synth.make_graph(workload, seed=42, n=n_s, e=e_s, device="cpu")
+    e = b.num_edges
+    q = int(e * SAMPLE_PERC)
+    f, c = b.x.size(1), b.num_classes
+    params = {k: v.requires_grad_(True) for k, v in ox.init_params(f, HIDDEN, c).items()}
+    og = torch.optim.Adam([p for n, p in params.items() if "gcn" in n], lr=1e-3)
+    oe = torch.optim.Adam([p for n, p in params.items() if "edge_prob_mlp" in n], lr=1e-3)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        og.zero_grad()
+        oe.zero_grad()
+        st = ox.learned_step(params, b, q, ox.exponential_noise(e), ox.exponential_noise(e), pipeline="hybrid",
+                             p_drop=drop_rate, chunk=1 << 16)
+        for k, g in st.grads.items():
+            params[k].grad = g
+        if st.branch == "learned":
+            oe.step()
+        og.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = sum(times)
+    return {"value": q * len(times) / t, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{workload} shape scaled {scale:g}x (N={b.num_nodes}, E={e}, q={q}, F={f}, H={HIDDEN}), "
+                      f"{len(times)} hybrid epochs of oracle/extended.learned_step + Adam, dropout {drop_rate}",
+            "ms_per_step": 1e3 * t / len(times), "q": q}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scale = a.cpu_scale
+    r = cpu_epochs(a.workload, scale, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": "sampled_edges_per_s", "value": r["value"], "unit": "edges/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{a.workload}-shape hybrid epoch (bounded CPU sample)", "sample": r["sample"],
+                       "hidden": HIDDEN, "sample_perc": SAMPLE_PERC},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+
+def run_gpu_arm(a):
+    import torch.distributed as dist
+    from sgs_gnn_b200 import _lib, ops, synth, training_hybrid
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(gemm=a.gemm_precision, scorer=a.precision)
+    _lib.lib()
+
+    # weak scaling: every rank trains on its own replica graph (seed differs per rank)
+    batch = synth.make_graph(a.workload, seed=42 + rank, device=dev, scale=a.scale)
+    n, e, f, c = batch.num_nodes, batch.num_edges, batch.x.size(1), batch.num_classes
+    q = int(e * SAMPLE_PERC)
+    model, og, oe, oa = build_model(f, c, dev, a.drop_rate)
+    args = make_args(dev, a.drop_rate)
+    crit = nn.CrossEntropyLoss()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def epoch(loader, ep):
+        return training_hybrid.train(args, ep, 1000, model, og, oe, oa, crit, loader, q=q, alternate_frequency=0)
+
+    # ---- resident arm ----
+    loader = [batch]
+    for w in range(a.warmup):
+        epoch(loader, 1 + w)
+    barrier()
+    launches0 = _lib.launch_count()
+    learned = 0
+    with ClockSampler(local) as clk, ops.KernelTimer() as kt:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for s in range(a.steps):
+            _, _, n_cond, _ = epoch(loader, 100 + s)
+            learned += n_cond
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        ktot = kt.totals_ms()
+    launches = _lib.launch_count() - launches0
+    clocks = clk.summary()
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * q * a.steps / (ms * 1e-3)
+
+    # ---- e2e arm: batch lives in pinned host memory, uploaded inside train() every step ----
+    e2e = None
+    if not a.no_e2e:
+        host = batch.to("cpu").pin_memory()
+        host._sgs_has_train = True
+        h2d = host.nbytes()
+        loader_h = [host]
+        for w in range(min(a.warmup, 2)):
+            epoch(loader_h, 1)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for s in range(a.steps):
+            epoch(loader_h, 200 + s)
+        ev1.record()
+        barrier()
+        ms_e = ev0.elapsed_time(ev1)
+        if world > 1:
+            tms = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_e = float(tms.item())
+        e2e = {"value": world * q * a.steps / (ms_e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 32 * 8 + 4, "ms_per_step": ms_e / a.steps}
+        del host, loader_h
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: edge scorer forward over all E edges ----
+    pk = peaks()
+    k1_ms, k1_n = ktot.get("edge_score_fwd", (0.0, 0))
+    flops_per_edge = 2 * (2 * HIDDEN) * HIDDEN + 2 * HIDDEN          # SURVEY 8(d)-bis K1 (concat form)
+    # one timed call scores all E edges (the hybrid backward's recompute is in edge_score_bwd)
+    k1_avg_s = (k1_ms / max(k1_n, 1)) * 1e-3
+    achieved = e * flops_per_edge / k1_avg_s / 1e12 if k1_avg_s > 0 else 0.0
+    roofline = {"kernel": "sgs_edge_score_fwd (K1, all E edges)", "bound": "tensor", "achieved": achieved,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
+                "peak_source": f"{pk['src']} bf16 sustained", "launches_timed": k1_n,
+                "avg_launch_ms": k1_ms / max(k1_n, 1),
+                "hbm_view": {"algorithmic_bytes": e * 1032 + n * 1028,
+                             "achieved_gbs": (e * 1032 + n * 1028) / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0,
+                             "peak_gbs": pk["hbm"]}}
+    shares = {k: round(v[0] / ms, 4) for k, v in sorted(ktot.items(), key=lambda kv: -kv[1][0])}
+
+    cpu = None
+    if not a.no_cpu:
+        cpu = cpu_epochs(a.workload, a.cpu_scale, 2, 1, a.drop_rate)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": "sampled_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32"}.get(a.precision, a.precision), "data": "synthetic",
+            "config": {"workload": f"{a.workload}-shape hybrid epoch, single full-graph batch" +
+                                   ("" if a.scale == 1.0 else f" (scaled {a.scale:g}x)"),
+                       "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
+                       "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": "hybrid",
+                       "conditional": True, "scorer_precision": a.precision, "gemm_precision": a.gemm_precision,
+                       "parallelism": "single" if world == 1 else f"replicas x{world}",
+                       "l2_policy": "inputs larger than L2 (graph + features >> 126 MB)",
+                       "learned_wins_steps": learned},
+            "epochs_per_s": world * a.steps / (ms * 1e-3), "scored_edges_per_s": world * e * a.steps / (ms * 1e-3),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "kernel_time_share": shares, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="reddit")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E of the GPU workload (debug only)")
+    ap.add_argument("--cpu-scale", type=float, default=1.0 / 128, help="bounded CPU sample: N, E scaled by this")
+    ap.add_argument("--precision", default=os.environ.get("SGS_SCORER_PRECISION", "fp32"),
+                    choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--gemm-precision", default=os.environ.get("SGS_GEMM_PRECISION", "fp32"),
+                    choices=["fp32", "bf16", "fp16", "tf32"])
+    ap.add_argument("--drop-rate", type=float, default=0.3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "b200":
+        print(f"note: warmup {a.warmup} < 3 breaks the timing rules", file=sys.stderr)
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()
