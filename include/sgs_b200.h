@@ -135,7 +135,8 @@ int32_t sgs_gemm(const float* A, int64_t a_sm, int64_t a_sk, const float* B, int
  * W1 is [H,2H] row-major, w2 [H], b2 [1].  The [E,2H] feature tensor is never materialised
  * in HBM in the tensor-core modes; the fp32 parity mode works in bounded chunks of `ws`.
  * ---------------------------------------------------------------------------------------- */
-size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t H, int32_t precision, int32_t backward);
+size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t N, int64_t H, int32_t precision,
+                                      int32_t backward);
 int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t* src,
                            const int32_t* dst, const int32_t* ids, int64_t n, const float* W1,
                            const float* b1, const float* w2, const float* b2, float p_drop,

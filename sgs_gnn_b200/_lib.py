@@ -36,7 +36,7 @@ SIGNATURES = {
     "sgs_colsum": (I32, [P, I64, I64, P, P]),
     "sgs_gcn_edge_grad": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, P]),
     "sgs_gemm": (I32, [P, I64, I64, P, I64, I64, P, I64, I64, I64, I64, I32, I32, P]),
-    "sgs_edge_score_workspace_bytes": (SZ, [I64, I64, I32, I32]),
+    "sgs_edge_score_workspace_bytes": (SZ, [I64, I64, I64, I32, I32]),
     "sgs_edge_score_fwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, SZ, I32, P]),
     "sgs_edge_score_bwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, P, P, P, P, SZ,
                                  I32, P]),

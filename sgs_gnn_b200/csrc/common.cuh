@@ -52,9 +52,16 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
-// 64 random bits for the 4 consecutive columns [4*col4, 4*col4+4) of `row`.
+// Per-row key, computed once per (seed, row); then 64 random bits for the 4 consecutive columns
+// [4*col4, 4*col4+4) of that row cost a single splitmix64.
+__host__ __device__ __forceinline__ uint64_t dropout_rowkey(uint64_t seed, uint64_t row) {
+  return splitmix64(seed + row * 0xD6E8FEB86659FD93ull);
+}
+__host__ __device__ __forceinline__ uint64_t dropout_bits_rk(uint64_t rowkey, uint32_t col4) {
+  return splitmix64(rowkey ^ ((uint64_t)col4 * 0xA0761D6478BD642Full));
+}
 __host__ __device__ __forceinline__ uint64_t dropout_bits(uint64_t seed, uint64_t row, uint32_t col4) {
-  return splitmix64(seed ^ splitmix64((row << 20) | (uint64_t)col4));
+  return dropout_bits_rk(dropout_rowkey(seed, row), col4);
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
   float t = p * 65536.0f + 0.5f;

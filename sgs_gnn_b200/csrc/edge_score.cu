@@ -188,9 +188,9 @@ using namespace sgs;
 
 extern "C" {
 
-size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t H, int32_t precision, int32_t backward) {
+size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t N, int64_t H, int32_t precision, int32_t backward) {
   if (n <= 0 || H <= 0) return 256;
-  if (precision != SGS_PREC_FP32 && !backward) return edge_score_tc_workspace_bytes(n, 0, H);
+  if (precision != SGS_PREC_FP32 && !backward) return edge_score_tc_workspace_bytes(n, N, H);
   const int64_t chunk = n < kMaxChunk ? n : kMaxChunk;
   return (size_t)chunk * per_edge_bytes(H, backward) + 256;
 }

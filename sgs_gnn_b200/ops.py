@@ -370,7 +370,7 @@ def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0,
     n_nodes, h = out.shape
     n = graph.num_edges if ids is None else int(ids.numel())
     p = torch.empty(n, dtype=torch.float32, device=out.device)
-    nbytes = lib().sgs_edge_score_workspace_bytes(n, h, prec, 0)
+    nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, prec, 0)
     ws = _ws(nbytes, out.device)
     with _timed("edge_score_fwd"):
         check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
@@ -411,7 +411,7 @@ class EdgeScoreFn(torch.autograd.Function):
         d_out = torch.zeros_like(out)
         dw1 = torch.zeros_like(w1)
         small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
-        nbytes = lib().sgs_edge_score_workspace_bytes(n, h, PREC_FP32, 1)
+        nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, PREC_FP32, 1)
         ws = _ws(nbytes, dev)
         with _timed("edge_score_bwd"):
             check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),

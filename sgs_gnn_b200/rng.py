@@ -26,6 +26,8 @@ def keep_mask(seed, rows, ncols, p):
     rows = np.asarray(rows, dtype=np.uint64).reshape(-1, 1)
     col4 = (np.arange(ncols, dtype=np.uint64) >> np.uint64(2)).reshape(1, -1)
     k = (np.arange(ncols, dtype=np.uint64) & np.uint64(3)).reshape(1, -1)
-    bits = splitmix64(np.uint64(seed) ^ splitmix64((rows << np.uint64(20)) | col4))
+    with np.errstate(over="ignore"):
+        rowkey = splitmix64(np.uint64(seed) + rows * np.uint64(0xD6E8FEB86659FD93))
+        bits = splitmix64(rowkey ^ (col4 * np.uint64(0xA0761D6478BD642F)))
     lane = (bits >> (np.uint64(16) * k)) & np.uint64(0xFFFF)
     return lane >= np.uint64(dropout_threshold(p))

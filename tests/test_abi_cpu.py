@@ -50,8 +50,8 @@ def test_workspace_queries_need_no_gpu():
     h = _lib.lib()
     assert h.sgs_csr_workspace_bytes(1000, 10) > 16000
     assert h.sgs_topq_workspace_bytes(1 << 20) >= 2 * 128 * 4
-    assert h.sgs_edge_score_workspace_bytes(1000, 256, 0, 0) >= 1000 * 3 * 256 * 4
-    assert h.sgs_edge_score_workspace_bytes(1000, 256, 0, 1) >= 1000 * 5 * 256 * 4
+    assert h.sgs_edge_score_workspace_bytes(1000, 50, 256, 0, 0) >= 1000 * 3 * 256 * 4
+    assert h.sgs_edge_score_workspace_bytes(1000, 50, 256, 0, 1) >= 1000 * 5 * 256 * 4
 
 
 def test_bad_arguments_return_error_codes_not_crashes():
