@@ -143,13 +143,15 @@ int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t
                            uint64_t seed, float* p, void* ws, size_t ws_bytes, int32_t precision,
                            sgs_stream_t stream);
 /* Backward over the same edge list given dp[n] (upstream dL/dp_e, compact: dp[i] belongs to
- * edge ids[i] or i).  Accumulates (+=) into d_out[N,H], dW1[H,2H], db1[H], dw2[H], db2[1]. */
+ * edge ids[i] or i).  Accumulates (+=) into d_out[N,H], dW1[H,2H], db1[H], dw2[H], db2[1].
+ * p_fwd[n]: the forward probabilities of these edges (required by the tensor-core modes, which
+ * use dz = dp*p*(1-p); the fp32 mode recomputes p and ignores it, may be NULL there). */
 int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t* src,
                            const int32_t* dst, const int32_t* ids, int64_t n, const float* W1,
                            const float* b1, const float* w2, const float* b2, float p_drop,
-                           uint64_t seed, const float* dp, float* d_out, float* dW1, float* db1,
-                           float* dw2, float* db2, void* ws, size_t ws_bytes, int32_t precision,
-                           sgs_stream_t stream);
+                           uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
+                           float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
+                           int32_t precision, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 sampler  (sampling.py:91-155 gumbel_softmax_sampling + the compaction at

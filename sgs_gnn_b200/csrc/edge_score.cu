@@ -12,6 +12,15 @@ int32_t edge_score_fwd_tc(const float* out, int64_t N, int64_t H, const int32_t*
                           const float* b2, float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes,
                           int32_t precision, cudaStream_t st);
 size_t edge_score_tc_workspace_bytes(int64_t n, int64_t N, int64_t H);
+size_t edge_score_bwd_tc_workspace_bytes(int64_t n, int64_t N, int64_t H);
+int32_t edge_score_bwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
+                          const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
+                          float p_drop, uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
+                          float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int32_t precision,
+                          cudaStream_t st);
+static inline bool tc_bwd_supported(int32_t precision, int64_t H) {
+  return (precision == SGS_PREC_BF16 || precision == SGS_PREC_FP16) && (H == 128 || H == 256);
+}
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
@@ -191,6 +200,7 @@ extern "C" {
 size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t N, int64_t H, int32_t precision, int32_t backward) {
   if (n <= 0 || H <= 0) return 256;
   if (precision != SGS_PREC_FP32 && !backward) return edge_score_tc_workspace_bytes(n, N, H);
+  if (backward && tc_bwd_supported(precision, H)) return edge_score_bwd_tc_workspace_bytes(n, N, H);
   const int64_t chunk = n < kMaxChunk ? n : kMaxChunk;
   return (size_t)chunk * per_edge_bytes(H, backward) + 256;
 }
@@ -229,8 +239,8 @@ int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t
 
 int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                            const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                           const float* b2, float p_drop, uint64_t seed, const float* dp, float* d_out,
-                           float* dW1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
+                           const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
+                           float* d_out, float* dW1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream) {
   SGS_CHECK_ARG(n >= 0 && N > 0 && H > 0 && H % 4 == 0, "bad sizes (H must be a multiple of 4)");
   if (n == 0) return SGS_OK;
@@ -238,8 +248,13 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
                 "null pointer");
   SGS_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "p_drop must be in [0,1)");
   SGS_CHECK_ARG(H <= 512, "backward supports H <= 512");
-  (void)precision;  // the backward currently always runs the fp32 path
   cudaStream_t st = as_stream(stream);
+  // tensor-core modes: fused tcgen05 kernels for H in {128, 256}; other widths keep the fp32 CUDA-core path
+  if (tc_bwd_supported(precision, H)) {
+    SGS_CHECK_ARG(p_fwd != nullptr, "tensor-core backward needs the forward probabilities p_fwd");
+    return edge_score_bwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, dw2,
+                             db2, ws, ws_bytes, precision, st);
+  }
   const size_t pe = per_edge_bytes(H, 1);
   int64_t chunk = (int64_t)((ws_bytes > 256 ? ws_bytes - 256 : 0) / pe);
   if (chunk > kMaxChunk) chunk = kMaxChunk;

@@ -148,4 +148,33 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 }  // namespace tc
+
+// 16-bit operand formats of kind::f16 MMAs
+template <typename T>
+struct Cvt;
+template <>
+struct Cvt<__nv_bfloat16> {
+  static constexpr int kFmt = 1;
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __device__ static __forceinline__ float2 unpack(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+};
+template <>
+struct Cvt<__half> {
+  static constexpr int kFmt = 0;
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __device__ static __forceinline__ float2 unpack(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+};
+
 }  // namespace sgs

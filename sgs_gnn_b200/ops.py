@@ -397,12 +397,13 @@ class EdgeScoreFn(torch.autograd.Function):
         else:
             p = precomputed
         ctx.graph, ctx.ids, ctx.p_drop, ctx.seed = graph, ids, p_drop, seed
-        ctx.save_for_backward(out, w1, b1, w2, b2)
+        ctx.prec = _state["scorer"] if precision is None else precision
+        ctx.save_for_backward(out, w1, b1, w2, b2, p)
         return p
 
     @staticmethod
     def backward(ctx, dp):
-        out, w1, b1, w2, b2 = ctx.saved_tensors
+        out, w1, b1, w2, b2, p_fwd = ctx.saved_tensors
         graph, ids = ctx.graph, ctx.ids
         dp = _req(dp, torch.float32, "grad")
         n_nodes, h = out.shape
@@ -411,13 +412,14 @@ class EdgeScoreFn(torch.autograd.Function):
         d_out = torch.zeros_like(out)
         dw1 = torch.zeros_like(w1)
         small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
-        nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, PREC_FP32, 1)
+        nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, ctx.prec, 1)
         ws = _ws(nbytes, dev)
         with _timed("edge_score_bwd"):
             check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
-                                           _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(dp),
-                                           _p(d_out), _p(dw1), _p(small), _p(small[h:]), _p(small[2 * h:]), _p(ws),
-                                           ws.numel(), _state["scorer"], _stream()), "sgs_edge_score_bwd")
+                                           _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(p_fwd),
+                                           _p(dp), _p(d_out), _p(dw1), _p(small), _p(small[h:]),
+                                           _p(small[2 * h:]), _p(ws), ws.numel(), ctx.prec, _stream()),
+                      "sgs_edge_score_bwd")
         db1, dw2, db2 = small[:h], small[h:2 * h].reshape(ctx.w2_shape), small[2 * h:].reshape(ctx.b2_shape)
         return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None
 

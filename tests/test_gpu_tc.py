@@ -54,3 +54,28 @@ def test_scorer_tc_forward_id_subset(dev, prec):
     sub = ops.edge_score_forward(args[0], graph, *args[1:], ids, 0.3, 99, ops._PRECISION[prec])
     # same edges, same dropout mask (keyed by edge id): identical up to accumulation order in TMEM
     assert float((sub - full[ids.long()]).abs().max()) <= 1e-6
+
+
+GBOUND = {"bf16": 2e-2, "fp16": 3e-3}   # max-norm relative error of gradients, 16-bit operands
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("h,e,subset,p_drop", [(256, 128, False, 0.0), (256, 5000, False, 0.3), (128, 3333, True, 0.3),
+                                               (256, 20011, True, 0.0)])
+def test_scorer_tc_backward_matches_fp32_path(dev, prec, h, e, subset, p_drop):
+    from sgs_gnn_b200 import ops
+    n_nodes = 600
+    ei, out, W1, b1, w2, b2 = _setup(n_nodes, e, h, h + e + 1)
+    graph = ops.graph_of(ei.to(dev), n_nodes)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.sort(torch.randperm(e, generator=g)[: max(1, e // 3)]).values.int().to(dev) if subset else None
+    n = e if ids is None else ids.numel()
+    gup = (torch.randn(n, generator=g) * 1e-6).to(dev)     # realistic tiny upstream gradients (mean over q)
+    grads = {}
+    for mode in ("fp32", prec):
+        leaves = [t.to(dev).clone().requires_grad_(True) for t in (out, W1, b1, w2.reshape(1, -1), b2)]
+        p = ops.edge_score(*leaves, graph, ids, p_drop, 1234, None, ops._PRECISION[mode])
+        grads[mode] = torch.autograd.grad((p * gup).sum(), leaves)
+    for name, a, r in zip(("d_out", "dW1", "db1", "dw2", "db2"), grads[prec], grads["fp32"]):
+        err = float((a - r).abs().max() / (r.abs().max() + 1e-30))
+        assert err <= GBOUND[prec], (name, prec, h, e, err)
