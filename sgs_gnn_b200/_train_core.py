@@ -30,7 +30,7 @@ def _softmax_prob(prob):
         return hit[2]
     s = ops.softmax_f32(prob)
     try:
-        _softmax_cache[key] = (weakref.ref(prob, lambda _r, k=key: _softmax_cache.pop(k, None)), prob._version, s)
+        _softmax_cache[key] = (weakref.ref(prob, lambda _r, k=key, c=_softmax_cache: c.pop(k, None)), prob._version, s)
     except TypeError:
         pass
     return s

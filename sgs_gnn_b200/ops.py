@@ -255,7 +255,7 @@ def graph_of(edge_index, num_nodes):
         return hit[2]
     g = Graph.from_edge_index(edge_index, num_nodes)
     try:
-        ref = weakref.ref(edge_index, lambda _r, k=key: _graph_cache.pop(k, None))
+        ref = weakref.ref(edge_index, lambda _r, k=key, c=_graph_cache: c.pop(k, None))
         _graph_cache[key] = (ref, edge_index._version, g)
     except TypeError:
         pass

@@ -56,26 +56,72 @@ def test_scorer_tc_forward_id_subset(dev, prec):
     assert float((sub - full[ids.long()]).abs().max()) <= 1e-6
 
 
-GBOUND = {"bf16": 2e-2, "fp16": 3e-3}   # max-norm relative error of gradients, 16-bit operands
+# Gradients, 16-bit operands.  Two checks:
+#  (1) against an fp32 emulation of the SAME quantised computation (operands rounded to 16 bit exactly where
+#      the kernels round them, fp32 accumulation): tight bound -- validates the tcgen05 kernels themselves;
+#  (2) against the fp32 CUDA-core parity path: looser stated bound, dominated by ReLU-mask flips of hidden
+#      units whose pre-activation is within rounding distance of zero (dw2 / db2, which are insensitive to
+#      flips, show the pure arithmetic error: ~3e-3 bf16, ~4e-4 fp16).
+L2BOUND_VS_FP32 = {"bf16": 8e-2, "fp16": 4e-2}
+L2BOUND_VS_EMUL = {"bf16": 3e-3, "fp16": 3e-3}
+TORCH_T = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def _l2rel(a, r):
+    a, r = a.flatten().double().cpu(), r.flatten().double().cpu()
+    return float((a - r).norm() / (r.norm() + 1e-300))
+
+
+def _emulated_grads(prec, out, ei, W1, b1, w2, b2, gup, keep, p_drop):
+    """fp32 CPU autograd of the quantised computation the TC kernels perform."""
+    dt = TORCH_T[prec]
+    ste = lambda t: t + (t.to(dt).float() - t).detach()
+    absmax = float(gup.abs().max())
+    S = 2.0 ** np.floor(np.log2(1024.0 / absmax))
+
+    class RoundGrad(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, z):
+            return z.view_as(z)
+
+        @staticmethod
+        def backward(ctx, g):
+            return (g * S).to(dt).float() / S
+
+    leaves = [t.clone().requires_grad_(True) for t in (out, W1, b1, w2.reshape(1, -1), b2)]
+    o, w1_, b1_, w2_, b2_ = leaves
+    oq = ste(o)
+    x, y = oq[ei[0]], oq[ei[1]]
+    feat = torch.cat([ste(x * y), ste(x - y)], 1)
+    z = RoundGrad.apply(feat @ ste(w1_).t())
+    hid = torch.relu(z + b1_)
+    if keep is not None:
+        hid = hid * keep / (1 - p_drop)
+    p = torch.sigmoid(hid @ w2_.t() + b2_).squeeze(-1)
+    return torch.autograd.grad((p * gup).sum(), leaves)
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("h,e,subset,p_drop", [(256, 128, False, 0.0), (256, 5000, False, 0.3), (128, 3333, True, 0.3),
                                                (256, 20011, True, 0.0)])
-def test_scorer_tc_backward_matches_fp32_path(dev, prec, h, e, subset, p_drop):
-    from sgs_gnn_b200 import ops
+def test_scorer_tc_backward(dev, prec, h, e, subset, p_drop):
+    from sgs_gnn_b200 import ops, rng
     n_nodes = 600
     ei, out, W1, b1, w2, b2 = _setup(n_nodes, e, h, h + e + 1)
     graph = ops.graph_of(ei.to(dev), n_nodes)
     g = torch.Generator().manual_seed(3)
-    ids = torch.sort(torch.randperm(e, generator=g)[: max(1, e // 3)]).values.int().to(dev) if subset else None
-    n = e if ids is None else ids.numel()
-    gup = (torch.randn(n, generator=g) * 1e-6).to(dev)     # realistic tiny upstream gradients (mean over q)
+    ids_c = torch.sort(torch.randperm(e, generator=g)[: max(1, e // 3)]).values if subset else torch.arange(e)
+    ids = ids_c.int().to(dev) if subset else None
+    n = ids_c.numel()
+    gup = torch.randn(n, generator=g) * 1e-6               # realistic tiny upstream gradients (mean over q)
+    seed = 1234
     grads = {}
     for mode in ("fp32", prec):
         leaves = [t.to(dev).clone().requires_grad_(True) for t in (out, W1, b1, w2.reshape(1, -1), b2)]
-        p = ops.edge_score(*leaves, graph, ids, p_drop, 1234, None, ops._PRECISION[mode])
-        grads[mode] = torch.autograd.grad((p * gup).sum(), leaves)
-    for name, a, r in zip(("d_out", "dW1", "db1", "dw2", "db2"), grads[prec], grads["fp32"]):
-        err = float((a - r).abs().max() / (r.abs().max() + 1e-30))
-        assert err <= GBOUND[prec], (name, prec, h, e, err)
+        p = ops.edge_score(*leaves, graph, ids, p_drop, seed, None, ops._PRECISION[mode])
+        grads[mode] = torch.autograd.grad((p * gup.to(dev)).sum(), leaves)
+    keep = torch.from_numpy(rng.keep_mask(seed, ids_c.numpy(), h, p_drop)).float() if p_drop > 0 else None
+    emul = _emulated_grads(prec, out, ei[:, ids_c], W1, b1, w2, b2, gup, keep, p_drop)
+    for name, a, r, em in zip(("d_out", "dW1", "db1", "dw2", "db2"), grads[prec], grads["fp32"], emul):
+        assert _l2rel(a, em) <= L2BOUND_VS_EMUL[prec], ("vs emulation", name, prec, h, e, _l2rel(a, em))
+        assert _l2rel(a, r) <= L2BOUND_VS_FP32[prec], ("vs fp32 path", name, prec, h, e, _l2rel(a, r))
