@@ -52,13 +52,23 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
-// Per-row key, computed once per (seed, row); then 64 random bits for the 4 consecutive columns
-// [4*col4, 4*col4+4) of that row cost a single splitmix64.
-__host__ __device__ __forceinline__ uint64_t dropout_rowkey(uint64_t seed, uint64_t row) {
-  return splitmix64(seed + row * 0xD6E8FEB86659FD93ull);
+// Dropout keep decisions: a 32-bit per-row key (one splitmix64 per (seed, row)), then one cheap 32-bit
+// mix per PAIR of columns whose two 16-bit halves are compared against the threshold.
+__host__ __device__ __forceinline__ uint32_t dropout_rowkey(uint64_t seed, uint64_t row) {
+  return (uint32_t)(splitmix64(seed + row * 0xD6E8FEB86659FD93ull) >> 32);
 }
-__host__ __device__ __forceinline__ uint64_t dropout_bits_rk(uint64_t rowkey, uint32_t col4) {
-  return splitmix64(rowkey ^ ((uint64_t)col4 * 0xA0761D6478BD642Full));
+// 32 random bits for columns (2*colpair, 2*colpair + 1): low half -> even column, high half -> odd column
+__host__ __device__ __forceinline__ uint32_t dropout_pair(uint32_t rowkey, uint32_t colpair) {
+  uint32_t h = rowkey ^ (colpair * 0x9E3779B9u);
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+// 64 bits = four 16-bit lanes for the 4 consecutive columns [4*col4, 4*col4 + 4)
+__host__ __device__ __forceinline__ uint64_t dropout_bits_rk(uint32_t rowkey, uint32_t col4) {
+  return (uint64_t)dropout_pair(rowkey, 2 * col4) | ((uint64_t)dropout_pair(rowkey, 2 * col4 + 1) << 32);
 }
 __host__ __device__ __forceinline__ uint64_t dropout_bits(uint64_t seed, uint64_t row, uint32_t col4) {
   return dropout_bits_rk(dropout_rowkey(seed, row), col4);

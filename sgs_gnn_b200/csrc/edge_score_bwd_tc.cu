@@ -213,19 +213,13 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
         uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t xs[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
-          const uint32_t ys[4] = {cy[i].x, cy[i].y, cy[i].z, cy[i].w};
-          uint32_t pr[4], df[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 xa = Cvt<T>::unpack(xs[k]);
-            const float2 ya = Cvt<T>::unpack(ys[k]);
-            pr[k] = Cvt<T>::pack(xa.x * ya.x, xa.y * ya.y);
-            df[k] = Cvt<T>::pack(xa.x - ya.x, xa.y - ya.y);
-          }
           const uint32_t off = sw128_offset(row_base + 32 * i, c);
-          *reinterpret_cast<uint4*>(stage + off) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-          *reinterpret_cast<uint4*>(stage + TILE_M * 128 + off) = make_uint4(df[0], df[1], df[2], df[3]);
+          *reinterpret_cast<uint4*>(stage + off) =
+              make_uint4(Cvt<T>::mul2(cx[i].x, cy[i].x), Cvt<T>::mul2(cx[i].y, cy[i].y),
+                         Cvt<T>::mul2(cx[i].z, cy[i].z), Cvt<T>::mul2(cx[i].w, cy[i].w));
+          *reinterpret_cast<uint4*>(stage + TILE_M * 128 + off) =
+              make_uint4(Cvt<T>::sub2(cx[i].x, cy[i].x), Cvt<T>::sub2(cx[i].y, cy[i].y),
+                         Cvt<T>::sub2(cx[i].z, cy[i].z), Cvt<T>::sub2(cx[i].w, cy[i].w));
         }
         fence_proxy_async_smem();
         mbar_arrive(full0 + 8 * slot);
@@ -326,7 +320,7 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
         dz = dp[i] * pe * (1.0f - pe);
       }
       if (ch == 0) acc_b2 += dz;
-      const uint64_t rowkey = drop ? dropout_rowkey(seed, (uint64_t)e) : 0ull;
+      const uint32_t rowkey = drop ? dropout_rowkey(seed, (uint64_t)e) : 0u;
       // ---- E1: Z -> dA ----
       mbar_wait(zfull0 + 8 * acc, (lt >> 1) & 1);
       tc_fence_after();
@@ -548,18 +542,10 @@ edge_score_bwd2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
           int64_t e = ids ? ids[i] : i;
           const uint4 xv = *reinterpret_cast<const uint4*>(tab + (int64_t)src[e] * H + cc * 8);
           const uint4 yv = *reinterpret_cast<const uint4*>(tab + (int64_t)dst[e] * H + cc * 8);
-          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-          const uint32_t ys[4] = {yv.x, yv.y, yv.z, yv.w};
-          uint32_t prr[4], dff[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 xa = Cvt<T>::unpack(xs[k]);
-            const float2 ya = Cvt<T>::unpack(ys[k]);
-            prr[k] = Cvt<T>::pack(xa.x * ya.x, xa.y * ya.y);
-            dff[k] = Cvt<T>::pack(xa.x - ya.x, xa.y - ya.y);
-          }
-          pr = make_uint4(prr[0], prr[1], prr[2], prr[3]);
-          df = make_uint4(dff[0], dff[1], dff[2], dff[3]);
+          pr = make_uint4(Cvt<T>::mul2(xv.x, yv.x), Cvt<T>::mul2(xv.y, yv.y), Cvt<T>::mul2(xv.z, yv.z),
+                          Cvt<T>::mul2(xv.w, yv.w));
+          df = make_uint4(Cvt<T>::sub2(xv.x, yv.x), Cvt<T>::sub2(xv.y, yv.y), Cvt<T>::sub2(xv.z, yv.z),
+                          Cvt<T>::sub2(xv.w, yv.w));
         }
         const int sp = cc >> 3;               // 64-column group
         const uint32_t off = sw128_offset(row, cc & 7);
@@ -631,10 +617,10 @@ __global__ void convert_rows_kernel_b(const float* __restrict__ in, int64_t n8, 
     const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
     const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
     uint4 o;
-    o.x = Cvt<T>::pack(a.x, a.y);
-    o.y = Cvt<T>::pack(a.z, a.w);
-    o.z = Cvt<T>::pack(b.x, b.y);
-    o.w = Cvt<T>::pack(b.z, b.w);
+    o.x = Cvt<T>::pack_table(a.x, a.y);
+    o.y = Cvt<T>::pack_table(a.z, a.w);
+    o.z = Cvt<T>::pack_table(b.x, b.y);
+    o.w = Cvt<T>::pack_table(b.z, b.w);
     outp[i] = o;
   }
 }

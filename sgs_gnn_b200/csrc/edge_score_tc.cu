@@ -39,10 +39,10 @@ __global__ void convert_rows_kernel(const float* __restrict__ in, int64_t n8, ui
     const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
     const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
     uint4 o;
-    o.x = Cvt<T>::pack(a.x, a.y);
-    o.y = Cvt<T>::pack(a.z, a.w);
-    o.z = Cvt<T>::pack(b.x, b.y);
-    o.w = Cvt<T>::pack(b.z, b.w);
+    o.x = Cvt<T>::pack_table(a.x, a.y);
+    o.y = Cvt<T>::pack_table(a.z, a.w);
+    o.z = Cvt<T>::pack_table(b.x, b.y);
+    o.w = Cvt<T>::pack_table(b.z, b.w);
     outp[i] = o;
   }
 }
@@ -142,9 +142,12 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
     o.w = Cvt<T>::pack(b.z, b.w);
     *reinterpret_cast<uint4*>(sm + (2 * sp + half) * B_BLOCK_BYTES + sw128_offset(nrow, c16)) = o;
   }
-  for (int j = threadIdx.x; j < BN; j += THREADS) {
-    b1s[j] = b1[nb * BN + j];
-    w2s[j] = w2[nb * BN + j];
+  {
+    const float w2_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;  // inverted-dropout scale folded into w2
+    for (int j = threadIdx.x; j < BN; j += THREADS) {
+      b1s[j] = b1[nb * BN + j];
+      w2s[j] = w2[nb * BN + j] * w2_scale;
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -190,19 +193,13 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
         uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t xs[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
-          const uint32_t ys[4] = {cy[i].x, cy[i].y, cy[i].z, cy[i].w};
-          uint32_t pr[4], df[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 xa = Cvt<T>::unpack(xs[k]);
-            const float2 ya = Cvt<T>::unpack(ys[k]);
-            pr[k] = Cvt<T>::pack(xa.x * ya.x, xa.y * ya.y);
-            df[k] = Cvt<T>::pack(xa.x - ya.x, xa.y - ya.y);
-          }
           const uint32_t off = sw128_offset(row_base + 32 * i, c);
-          *reinterpret_cast<uint4*>(stage + off) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-          *reinterpret_cast<uint4*>(stage + TILE_M * 128 + off) = make_uint4(df[0], df[1], df[2], df[3]);
+          *reinterpret_cast<uint4*>(stage + off) =
+              make_uint4(Cvt<T>::mul2(cx[i].x, cy[i].x), Cvt<T>::mul2(cx[i].y, cy[i].y),
+                         Cvt<T>::mul2(cx[i].z, cy[i].z), Cvt<T>::mul2(cx[i].w, cy[i].w));
+          *reinterpret_cast<uint4*>(stage + TILE_M * 128 + off) =
+              make_uint4(Cvt<T>::sub2(cx[i].x, cy[i].x), Cvt<T>::sub2(cx[i].y, cy[i].y),
+                         Cvt<T>::sub2(cx[i].z, cy[i].z), Cvt<T>::sub2(cx[i].w, cy[i].w));
         }
         fence_proxy_async_smem();
         mbar_arrive(full0 + 8 * slot);
@@ -253,13 +250,12 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
     const int r = lg * 32 + lane;  // row of the tile == TMEM lane
     const uint32_t thr = dropout_threshold(p_drop);
     const bool drop = p_drop > 0.f;
-    const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
     const float bias2 = b2[0];
     uint32_t lt = 0;
     for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
       const uint32_t acc = lt & 1;
       const int64_t i = t * TILE_M + r;
-      uint64_t rowkey = 0;
+      uint32_t rowkey = 0;
       if (drop) {
         int64_t e = i < n ? i : n - 1;
         if (ids) e = ids[e];
@@ -276,13 +272,24 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const int col = ch * CW + c0 + j4 * 4;  // column inside this CTA's hidden block
-          uint64_t bits = 0;
-          if (drop) bits = dropout_bits_rk(rowkey, (uint32_t)((nb * BN + col) >> 2));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float hv = fmaxf(__uint_as_float(v[j4 * 4 + k]) + b1s[col + k], 0.f);
-            if (drop) hv = dropout_keep(bits, k, thr) ? hv * scale : 0.f;
-            z = fmaf(w2s[col + k], hv, z);
+          const float4 bb = *reinterpret_cast<const float4*>(b1s + col);
+          const float4 ww = *reinterpret_cast<const float4*>(w2s + col);  // already scaled by 1/(1-p)
+          const float h0 = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bb.x, 0.f);
+          const float h1 = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bb.y, 0.f);
+          const float h2 = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bb.z, 0.f);
+          const float h3 = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bb.w, 0.f);
+          if (drop) {
+            const uint32_t cp = (uint32_t)(nb * BN + col) >> 1;
+            const uint32_t r0 = dropout_pair(rowkey, cp), r1 = dropout_pair(rowkey, cp + 1);
+            if ((r0 & 0xFFFFu) >= thr) z = fmaf(ww.x, h0, z);
+            if ((r0 >> 16) >= thr) z = fmaf(ww.y, h1, z);
+            if ((r1 & 0xFFFFu) >= thr) z = fmaf(ww.z, h2, z);
+            if ((r1 >> 16) >= thr) z = fmaf(ww.w, h3, z);
+          } else {
+            z = fmaf(ww.x, h0, z);
+            z = fmaf(ww.y, h1, z);
+            z = fmaf(ww.z, h2, z);
+            z = fmaf(ww.w, h3, z);
           }
         }
       }

@@ -149,7 +149,8 @@ __device__ __forceinline__ bool elect_one() {
 
 }  // namespace tc
 
-// 16-bit operand formats of kind::f16 MMAs
+// 16-bit operand formats of kind::f16 MMAs.  Packed arithmetic (HMUL2 / HSUB2) builds the edge features
+// directly on the gathered 16-bit pairs: one instruction per two columns, one rounding per result.
 template <typename T>
 struct Cvt;
 template <>
@@ -159,21 +160,41 @@ struct Cvt<__nv_bfloat16> {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  // node-embedding table entries (bf16 has fp32's range: no clamp needed)
+  __device__ static __forceinline__ uint32_t pack_table(float a, float b) { return pack(a, b); }
   __device__ static __forceinline__ float2 unpack(uint32_t u) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+  __device__ static __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ uint32_t sub2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
   }
 };
 template <>
 struct Cvt<__half> {
   static constexpr int kFmt = 0;
   __device__ static __forceinline__ uint32_t pack(float a, float b) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  // node-embedding table entries are clamped to |v| <= 255 so that x*y (<= 65025) can never overflow fp16
+  __device__ static __forceinline__ uint32_t pack_table(float a, float b) {
+    return pack(fminf(fmaxf(a, -255.f), 255.f), fminf(fmaxf(b, -255.f), 255.f));
+  }
   __device__ static __forceinline__ float2 unpack(uint32_t u) {
     return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+  __device__ static __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
+    __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ uint32_t sub2(uint32_t a, uint32_t b) {
+    __half2 r = __hsub2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
   }
 };
 

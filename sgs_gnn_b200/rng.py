@@ -21,13 +21,23 @@ def dropout_threshold(p):
     return 0 if t <= 0 else (65536 if t >= 65536 else int(t))
 
 
-def keep_mask(seed, rows, ncols, p):
-    """bool [len(rows), ncols]: keep decisions for (row id, column) exactly as dropout_keep()."""
-    rows = np.asarray(rows, dtype=np.uint64).reshape(-1, 1)
-    col4 = (np.arange(ncols, dtype=np.uint64) >> np.uint64(2)).reshape(1, -1)
-    k = (np.arange(ncols, dtype=np.uint64) & np.uint64(3)).reshape(1, -1)
+def _pair_hash(rowkey, colpair):
     with np.errstate(over="ignore"):
-        rowkey = splitmix64(np.uint64(seed) + rows * np.uint64(0xD6E8FEB86659FD93))
-        bits = splitmix64(rowkey ^ (col4 * np.uint64(0xA0761D6478BD642F)))
-    lane = (bits >> (np.uint64(16) * k)) & np.uint64(0xFFFF)
-    return lane >= np.uint64(dropout_threshold(p))
+        h = rowkey ^ (colpair * np.uint32(0x9E3779B9))
+        h = h * np.uint32(0x85EBCA6B)
+        h = h ^ (h >> np.uint32(13))
+        h = h * np.uint32(0xC2B2AE35)
+        h = h ^ (h >> np.uint32(16))
+    return h
+
+
+def keep_mask(seed, rows, ncols, p):
+    """bool [len(rows), ncols]: keep decisions for (row id, column) exactly as the kernels compute them
+    (dropout_rowkey / dropout_pair in csrc/common.cuh)."""
+    rows = np.asarray(rows, dtype=np.uint64).reshape(-1, 1)
+    with np.errstate(over="ignore"):
+        rowkey = (splitmix64(np.uint64(seed) + rows * np.uint64(0xD6E8FEB86659FD93)) >> np.uint64(32)).astype(np.uint32)
+    cols = np.arange(ncols, dtype=np.uint32).reshape(1, -1)
+    h = _pair_hash(rowkey, cols >> np.uint32(1))
+    lane = np.where((cols & np.uint32(1)) == 0, h & np.uint32(0xFFFF), h >> np.uint32(16))
+    return lane >= np.uint32(dropout_threshold(p))
