@@ -1,25 +1,27 @@
-// K1b tensor-core backward of the edge scorer, two fused kernels (nothing of size [q, H] or [q, 2H]
-// is written to HBM except the 16-bit dA needed by the dW1 kernel):
+// K1b tensor-core backward of the edge scorer: three fused tcgen05 kernels.  Nothing of size [q, 2H] is ever
+// written to HBM; the only intermediate is the 16-bit dA [q, H] (hidden-layer gradient).
 //
-//  B1  per 128-edge tile and per block of BN hidden units (CTA kind, W1 block resident in smem):
-//        MMA1: Z  = F . W1blk^T                      (recompute, as the forward kernel)
-//        E1  : dA = dz * w2 * keep * [Z+b1>0] (16-bit, scaled by S) -> smem + HBM; dw2, db1, db2
-//        MMA2: dF = dA . W1blk   (the SAME smem bytes of W1blk, read as an MN-major operand)
-//        E2  : d_out[src] += dF1*y + dF2 ; d_out[dst] += dF1*x - dF2     (128-bit vector RED)
-//  B2  dW1blk[BN, 2H] += dA^T . F : both operands are the row-major-by-edge tiles read as MN-major,
-//        the [BN x 2H] fp32 accumulator lives in TMEM for the whole kernel (512 columns).
+//  BA  (per 128-edge tile, per block of BN hidden units; W1 block resident in smem, as the forward):
+//        MMA : Z  = F . W1blk^T                              (recompute)
+//        EPI : dA = S * dz * w2 * keep * [Z + b1 > 0]  -> HBM (16 bit);  dw2, db1, db2 (warp transpose-reduce)
+//  BF  (per 128-edge tile, per block of 128 node-embedding columns; W1[:, cols] resident in smem and read as an
+//       MN-major operand -- the row-major bytes "transposed" by the descriptor):
+//        MMA : dF = dA . W1[:, cols]                          (K = H hidden units)
+//        EPI : d_out[src] += dF1*y + dF2  (segment-reduced over equal-src rows of a warp, then one coalesced RED)
+//              d_out[dst] += dF1*x - dF2  (128-bit vector RED)
+//  BW  dW1blk[BN, 2H] += dA^T . F : both operands are edge-major tiles read as MN-major; the [BN x 2H] fp32
+//        accumulator stays in TMEM (512 columns) for the whole kernel.
 //
-// dz = dp * p * (1 - p) uses the forward probability p saved by the caller, so the two hidden-unit
-// blocks never have to exchange partial logits.  S = 2^k (from max|dp|) keeps fp16 dA in range.
+// dz = dp * p * (1 - p) uses the forward probability saved by the caller.  S = 2^k (from max|dp|) keeps fp16 dA
+// in range; it is divided out again in the epilogues.
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace sgs {
 
-
 namespace kb {
 constexpr int TILE_M = 128;
-constexpr int STAGE_BYTES = TILE_M * 128 * 2;  // 32 KB: [128 x 64] product block + [128 x 64] difference block
+constexpr int STAGE_BYTES = TILE_M * 128 * 2;  // 32 KB: two [128 x 64] 16-bit blocks
 constexpr int EPI_WARPS = 8;
 constexpr int PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;
@@ -28,23 +30,6 @@ constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 }  // namespace kb
-
-// MN-major SWIZZLE_128B operand: 64-element (128 B) blocks along MN are `lbo` bytes apart, 8-row groups
-// along K are 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
 
 // in-warp transpose-reduce: every lane holds v[0..31] (one row, 32 columns); on return lane L holds the sum over
 // the 32 lanes (rows) of column L.  31 shuffles (recursive halving).
@@ -61,6 +46,20 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
   }
   return v[0];
 }
+// 16 columns per lane: lanes L and L^16 both end with the sum over all 32 rows of column (L & 15).
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = upper ? v[j] : v[j + half];
+      const float keep = upper ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
 
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
   float m = 0.f;
@@ -76,27 +75,41 @@ __device__ __forceinline__ float grad_scale(float absmax) {
   return exp2f(floorf(log2f(1024.0f / absmax)));
 }
 
+template <typename T>
+__global__ void convert_rows_kernel_b(const float* __restrict__ in, int64_t n8, uint4* __restrict__ outp) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n8; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    uint4 o;
+    o.x = Cvt<T>::pack_table(a.x, a.y);
+    o.y = Cvt<T>::pack_table(a.z, a.w);
+    o.z = Cvt<T>::pack_table(b.x, b.y);
+    o.w = Cvt<T>::pack_table(b.z, b.w);
+    outp[i] = o;
+  }
+}
+
 // =============================================================================================
-// B1
+// BA: recompute + hidden-layer gradient
 // =============================================================================================
 template <typename T, int BN, int H>
 __global__ void __launch_bounds__(kb::THREADS, 1)
-edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-                       const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
-                       const float* __restrict__ b1, const float* __restrict__ w2, float p_drop, uint64_t seed,
-                       const float* __restrict__ p_fwd, const float* __restrict__ dp,
-                       const float* __restrict__ dp_absmax, float* __restrict__ d_out, T* __restrict__ dA_out,
-                       float* __restrict__ dw2, float* __restrict__ db1, float* __restrict__ db2) {
+edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                         const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
+                         const float* __restrict__ b1, const float* __restrict__ w2, float p_drop, uint64_t seed,
+                         const float* __restrict__ p_fwd, const float* __restrict__ dp,
+                         const float* __restrict__ dp_absmax, T* __restrict__ dA_out, float* __restrict__ dw2,
+                         float* __restrict__ db1, float* __restrict__ db2) {
   using namespace kb;
   using namespace tc;
   constexpr int NB = H / BN;
-  constexpr int NSP = H / 64;               // F stage pairs per tile (MMA1) == dF column groups (MMA2)
-  constexpr int NSTAGE = 2;
+  constexpr int NSP = H / 64;
+  constexpr int NSTAGE = 3;
   constexpr int B_BLOCK_BYTES = BN * 128;
   constexpr int B_BYTES = 2 * NSP * B_BLOCK_BYTES;
-  constexpr int DA_BYTES = TILE_M * BN * 2;  // BN/64 blocks of [128 x 64]
-  constexpr int Z_COLS = BN;
-  constexpr int DF0 = 2 * Z_COLS;            // first dF buffer column
+  constexpr int TMEM_COLS = 2 * BN;
   static_assert(H % 64 == 0 && BN * NB == H && BN % 64 == 0 && BN <= 128, "unsupported shape");
 
   extern __shared__ uint8_t smem_raw[];
@@ -104,7 +117,7 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* sm = smem_raw + pad;
   const uint32_t sm_addr = raw_addr + pad;
-  constexpr uint32_t kUsed = B_BYTES + NSTAGE * STAGE_BYTES + DA_BYTES + BN * 8 + 16 * 8 + 16;
+  constexpr uint32_t kUsed = B_BYTES + NSTAGE * STAGE_BYTES + BN * 8 + 16 * 8 + 16;
   {
     uint32_t dyn_size;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
@@ -112,15 +125,12 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
   }
   const uint32_t b_base = sm_addr;
   const uint32_t a_base = b_base + B_BYTES;
-  const uint32_t da_base = a_base + NSTAGE * STAGE_BYTES;
-  uint8_t* da_ptr = sm + B_BYTES + NSTAGE * STAGE_BYTES;
-  float* b1s = reinterpret_cast<float*>(da_ptr + DA_BYTES);
+  float* b1s = reinterpret_cast<float*>(sm + B_BYTES + NSTAGE * STAGE_BYTES);
   float* w2s = b1s + BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w2s + BN);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t full0 = bar0, empty0 = bar0 + 16, zfull0 = bar0 + 32, zempty0 = bar0 + 48, dffull0 = bar0 + 64,
-                 dfempty0 = bar0 + 80, da_ready = bar0 + 96, da_free = bar0 + 104;
+  const uint32_t full0 = bar0, empty0 = bar0 + 32, zfull0 = bar0 + 64, zempty0 = bar0 + 80;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,20 +140,18 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
   const int64_t tstep = gridDim.x / NB;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full0 + 8 * s, PROD_THREADS);
       mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(zfull0 + 8 * s, 1);
       mbar_init(zempty0 + 8 * s, EPI_THREADS);
-      mbar_init(dffull0 + 8 * s, 1);
-      mbar_init(dfempty0 + 8 * s, EPI_THREADS);
     }
-    mbar_init(da_ready, EPI_THREADS);
-    mbar_init(da_free, 1);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
-    tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    tmem_alloc(smem_u32(tmem_ptr_s), TMEM_COLS);
     tmem_relinquish();
   }
   for (int idx = threadIdx.x; idx < BN * (2 * H / 8); idx += THREADS) {
@@ -177,7 +185,7 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
   const float invS = 1.0f / S;
 
   if (warp >= PROD_WARP0) {
-    // =============================== producers (identical to the forward) ===============================
+    // ------------------------------- producers (as the forward) -------------------------------
     const int pt = threadIdx.x - PROD_WARP0 * 32;
     const int c = pt & 7;
     const int row_base = pt >> 3;
@@ -233,16 +241,14 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
       }
     }
   } else if (warp == MMA_WARP) {
-    // =============================== MMA issuer ===============================
     if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc(Cvt<T>::kFmt, TILE_M, BN);
-      const uint32_t idesc2 = umma_idesc(Cvt<T>::kFmt, TILE_M, 128) | (1u << 16);  // B is MN-major
-      uint32_t it = 0;
-      auto mma1 = [&](uint32_t lt) {
+      const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, TILE_M, BN);
+      uint32_t it = 0, lt = 0;
+      for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
         const uint32_t acc = lt & 1;
         mbar_wait(zempty0 + 8 * acc, ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Z_COLS;
+        const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll 1
         for (int sp = 0; sp < NSP; ++sp, ++it) {
           const uint32_t slot = it % NSTAGE;
@@ -254,50 +260,19 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint64_t ad = umma_desc_k_sw128(a_base + slot * STAGE_BYTES + half * (TILE_M * 128) + k16 * 32);
               const uint64_t bd = umma_desc_k_sw128(b_base + (2 * sp + half) * B_BLOCK_BYTES + k16 * 32);
-              umma_f16(d_tmem, ad, bd, idesc1, (sp | half | k16) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, ad, bd, idesc, (sp | half | k16) != 0 ? 1u : 0u);
             }
           umma_commit(empty0 + 8 * slot);
         }
         umma_commit(zfull0 + 8 * acc);
-      };
-      auto mma2 = [&](uint32_t lt, int qd) {
-        const uint32_t g = lt * NSP + qd;
-        const uint32_t buf = g & 1;
-        mbar_wait(dfempty0 + 8 * buf, ((g >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + DF0 + buf * 128;
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t ad = umma_desc_k_sw128(da_base + (kk >> 2) * (TILE_M * 128) + (kk & 3) * 32);
-          const uint64_t bd = umma_desc_mn_sw128(b_base + (2 * qd) * B_BLOCK_BYTES + kk * 2048, B_BLOCK_BYTES);
-          umma_f16(d_tmem, ad, bd, idesc2, kk != 0 ? 1u : 0u);
-        }
-        umma_commit(dffull0 + 8 * buf);
-      };
-      uint32_t lt = 0;
-      if (tile0 < ntiles) mma1(0);
-      for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
-        mbar_wait(da_ready, lt & 1);
-        tc_fence_after();
-        const bool more = (t + tstep) < ntiles;
-        if (NSP >= 2) {
-          mma2(lt, 0);
-          mma2(lt, 1);
-          if (more) mma1(lt + 1);
-          for (int qd = 2; qd < NSP; ++qd) mma2(lt, qd);
-        } else {
-          mma2(lt, 0);
-          if (more) mma1(lt + 1);
-        }
-        umma_commit(da_free);
       }
     }
     __syncwarp();
   } else {
-    // =============================== epilogue (E1 + E2) ===============================
+    // ------------------------------- epilogue: Z -> dA, parameter gradients -------------------------------
     const int lg = warp & 3;
     const int ch = warp >> 2;
-    constexpr int CW = BN / 2;      // Z columns per epilogue warp (64 or 32)
+    constexpr int CW = BN / 2;
     const int r = lg * 32 + lane;
     const uint32_t thr = dropout_threshold(p_drop);
     const bool drop = p_drop > 0.f;
@@ -311,113 +286,66 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
       const uint32_t acc = lt & 1;
       const int64_t i = t * TILE_M + r;
       const bool live = i < n;
-      int64_t e = live ? i : n - 1;
-      if (ids) e = ids[e];
-      const int64_t s_node = src[e], d_node = dst[e];
       float dz = 0.f;
+      uint32_t rowkey = 0;
       if (live) {
         const float pe = p_fwd[i];
         dz = dp[i] * pe * (1.0f - pe);
+        if (drop) rowkey = dropout_rowkey(seed, (uint64_t)(ids ? ids[i] : i));
       }
       if (ch == 0) acc_b2 += dz;
-      const uint32_t rowkey = drop ? dropout_rowkey(seed, (uint64_t)e) : 0u;
-      // ---- E1: Z -> dA ----
+      const float dzs = dz * S;
       mbar_wait(zfull0 + 8 * acc, (lt >> 1) & 1);
       tc_fence_after();
-      mbar_wait(da_free, (lt & 1) ^ 1);  // MMA2 of the previous tile no longer reads the dA tile
-      const float dzs = dz * S;
 #pragma unroll
       for (int c0 = 0; c0 < CW; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + acc * Z_COLS + ch * CW + c0, v);
+        tmem_ld32(tmem_base + lane_off + acc * BN + ch * CW + c0, v);
         tmem_ld_wait();
+        if (c0 + 32 >= CW) {  // accumulator fully read
+          tc_fence_before();
+          mbar_arrive(zempty0 + 8 * acc);
+        }
         float hw[32], da[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const int col = ch * CW + c0 + j4 * 4;
-          uint64_t bits = 0;
-          if (drop) bits = dropout_bits_rk(rowkey, (uint32_t)((nb * BN + col) >> 2));
+          const float4 bb = *reinterpret_cast<const float4*>(b1s + col);
+          const float4 ww = *reinterpret_cast<const float4*>(w2s + col);
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+          const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+          uint32_t r0 = 0xFFFFFFFFu, r1 = 0xFFFFFFFFu;
+          if (drop) {
+            const uint32_t cp = (uint32_t)(nb * BN + col) >> 1;
+            r0 = dropout_pair(rowkey, cp);
+            r1 = dropout_pair(rowkey, cp + 1);
+          }
+          const bool keep[4] = {(r0 & 0xFFFFu) >= thr, (r0 >> 16) >= thr, (r1 & 0xFFFFu) >= thr, (r1 >> 16) >= thr};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float pre = __uint_as_float(v[j4 * 4 + k]) + b1s[col + k];
-            const bool on = pre > 0.f && (!drop || dropout_keep(bits, k, thr));
-            const float m = on ? scale : 0.f;
-            hw[j4 * 4 + k] = dz * (pre * m);              // dz * hidden  -> dw2
-            da[j4 * 4 + k] = dzs * w2s[col + k] * m;      // scaled dA
+            const float pre = __uint_as_float(v[j4 * 4 + k]) + bv[k];
+            const float m = (pre > 0.f && (!drop || keep[k])) ? scale : 0.f;
+            hw[j4 * 4 + k] = dz * (pre * m);       // dz * hidden  -> dw2
+            da[j4 * 4 + k] = dzs * wv[k] * m;      // scaled dA
           }
         }
-        // 16-bit dA: smem tile (A operand of MMA2) and HBM (operand of the dW1 kernel)
+        if (live) {
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint4 o;
-          o.x = Cvt<T>::pack(da[c8 * 8 + 0], da[c8 * 8 + 1]);
-          o.y = Cvt<T>::pack(da[c8 * 8 + 2], da[c8 * 8 + 3]);
-          o.z = Cvt<T>::pack(da[c8 * 8 + 4], da[c8 * 8 + 5]);
-          o.w = Cvt<T>::pack(da[c8 * 8 + 6], da[c8 * 8 + 7]);
-          const int col = ch * CW + c0 + c8 * 8;  // column inside the BN block
-          *reinterpret_cast<uint4*>(da_ptr + (col >> 6) * (TILE_M * 128) + sw128_offset(r, (col & 63) >> 3)) = o;
-          if (live) *reinterpret_cast<uint4*>(dA_out + (int64_t)i * H + nb * BN + col) = o;
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint4 o;
+            o.x = Cvt<T>::pack(da[c8 * 8 + 0], da[c8 * 8 + 1]);
+            o.y = Cvt<T>::pack(da[c8 * 8 + 2], da[c8 * 8 + 3]);
+            o.z = Cvt<T>::pack(da[c8 * 8 + 4], da[c8 * 8 + 5]);
+            o.w = Cvt<T>::pack(da[c8 * 8 + 6], da[c8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(dA_out + i * H + nb * BN + ch * CW + c0 + c8 * 8) = o;
+          }
         }
-        // column sums over the 32 rows of this warp (unscaled)
 #pragma unroll
         for (int j = 0; j < 32; ++j) da[j] *= invS;
         acc_w2[c0 / 32] += warp_colsum32(hw, lane);
         acc_b1[c0 / 32] += warp_colsum32(da, lane);
       }
-      tc_fence_before();
-      mbar_arrive(zempty0 + 8 * acc);
-      fence_proxy_async_smem();
-      mbar_arrive(da_ready);
-      // ---- E2: dF column groups -> scatter into d_out ----
-      const T* xrow = tab + s_node * H;
-      const T* yrow = tab + d_node * H;
-      float* dxrow = d_out + s_node * H;
-      float* dyrow = d_out + d_node * H;
-#pragma unroll 1
-      for (int qd = 0; qd < NSP; ++qd) {
-        const uint32_t g = lt * NSP + qd;
-        const uint32_t buf = g & 1;
-        const int col0 = qd * 64 + ch * 32;  // node-embedding columns handled by this thread
-        uint4 xv[4], yv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          xv[k] = *reinterpret_cast<const uint4*>(xrow + col0 + k * 8);
-          yv[k] = *reinterpret_cast<const uint4*>(yrow + col0 + k * 8);
-        }
-        mbar_wait(dffull0 + 8 * buf, (g >> 1) & 1);
-        tc_fence_after();
-        uint32_t f1[32], f2[32];
-        tmem_ld32(tmem_base + lane_off + DF0 + buf * 128 + ch * 32, f1);
-        tmem_ld32(tmem_base + lane_off + DF0 + buf * 128 + 64 + ch * 32, f2);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(dfempty0 + 8 * buf);
-        if (live) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t xs[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
-            const uint32_t ys[4] = {yv[k].x, yv[k].y, yv[k].z, yv[k].w};
-            float gx[8], gy[8];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const float2 xa = Cvt<T>::unpack(xs[m]);
-              const float2 ya = Cvt<T>::unpack(ys[m]);
-              const float a0 = __uint_as_float(f1[k * 8 + 2 * m]) * invS, a1 = __uint_as_float(f1[k * 8 + 2 * m + 1]) * invS;
-              const float c0_ = __uint_as_float(f2[k * 8 + 2 * m]) * invS, c1_ = __uint_as_float(f2[k * 8 + 2 * m + 1]) * invS;
-              gx[2 * m] = fmaf(a0, ya.x, c0_);
-              gx[2 * m + 1] = fmaf(a1, ya.y, c1_);
-              gy[2 * m] = fmaf(a0, xa.x, -c0_);
-              gy[2 * m + 1] = fmaf(a1, xa.y, -c1_);
-            }
-            red_add_v4(dxrow + col0 + k * 8, gx[0], gx[1], gx[2], gx[3]);
-            red_add_v4(dxrow + col0 + k * 8 + 4, gx[4], gx[5], gx[6], gx[7]);
-            red_add_v4(dyrow + col0 + k * 8, gy[0], gy[1], gy[2], gy[3]);
-            red_add_v4(dyrow + col0 + k * 8 + 4, gy[4], gy[5], gy[6], gy[7]);
-          }
-        }
-      }
     }
-    // flush the small parameter gradients: lane L holds column (ch*CW + 32*k + L) of this CTA's block
 #pragma unroll
     for (int k = 0; k < CW / 32; ++k) {
       const int col = nb * BN + ch * CW + 32 * k + lane;
@@ -434,29 +362,259 @@ edge_score_bwd1_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
   __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =============================================================================================
+// BF: dF = dA . W1[:, column block]  and the scatter into d_out
+// =============================================================================================
+template <typename T, int H>
+__global__ void __launch_bounds__(kb::THREADS, 1)
+edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                         const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
+                         const T* __restrict__ dA, const float* __restrict__ dp_absmax, float* __restrict__ d_out) {
+  using namespace kb;
+  using namespace tc;
+  constexpr int CB = 128;                       // node-embedding columns per CTA kind
+  constexpr int NKIND = H / CB;
+  constexpr int NQ = CB / 64;                   // 64-column groups (each: product block + difference block)
+  constexpr int BLK = H * 128;                  // one [H rows (j) x 64 k] 16-bit block
+  constexpr int B_BYTES = 2 * NQ * BLK;
+  constexpr int NJ = H / 128;                   // dA sub-tiles (128 hidden units each) per edge tile
+  constexpr int NSTAGE = 3;
+  static_assert(H % 128 == 0 && H <= 256, "unsupported shape");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* sm = smem_raw + pad;
+  const uint32_t sm_addr = raw_addr + pad;
+  constexpr uint32_t kUsed = B_BYTES + NSTAGE * STAGE_BYTES + 16 * 8 + 16;
+  {
+    uint32_t dyn_size;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
+    if (pad + kUsed > dyn_size) __trap();
+  }
+  const uint32_t b_base = sm_addr;
+  const uint32_t a_base = b_base + B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + B_BYTES + NSTAGE * STAGE_BYTES);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t full0 = bar0, empty0 = bar0 + 32, dffull0 = bar0 + 64, dfempty0 = bar0 + 80;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kind = blockIdx.x % NKIND;
+  const int64_t ntiles = (n + TILE_M - 1) / TILE_M;
+  const int64_t tile0 = blockIdx.x / NKIND;
+  const int64_t tstep = gridDim.x / NKIND;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full0 + 8 * s, PROD_THREADS);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(dffull0 + 8 * s, 1);
+      mbar_init(dfempty0 + 8 * s, EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    tmem_relinquish();
+  }
+  // resident operand: rows j = 0..H-1 of W1, this kind's columns, as blocks [H x 64]:
+  //   block 2*qd   : product-part columns    kind*CB + 64*qd + [0,64)
+  //   block 2*qd+1 : difference-part columns H + kind*CB + 64*qd + [0,64)
+  for (int idx = threadIdx.x; idx < H * (2 * CB / 8); idx += THREADS) {
+    const int j = idx / (2 * CB / 8);
+    const int kc = idx % (2 * CB / 8);          // 16-byte chunk among this kind's 2*CB columns
+    const int blk = kc >> 3;                    // 0 .. 2*NQ-1 in (qd, half) order: blk = 2*qd + half
+    const int qd = blk >> 1, half = blk & 1;
+    const int c16 = kc & 7;
+    const int kcol = (half ? H : 0) + kind * CB + qd * 64 + c16 * 8;
+    const float* g = W1 + (int64_t)j * (2 * H) + kcol;
+    const float4 a = *reinterpret_cast<const float4*>(g);
+    const float4 b = *reinterpret_cast<const float4*>(g + 4);
+    uint4 o;
+    o.x = Cvt<T>::pack(a.x, a.y);
+    o.y = Cvt<T>::pack(a.z, a.w);
+    o.z = Cvt<T>::pack(b.x, b.y);
+    o.w = Cvt<T>::pack(b.z, b.w);
+    *reinterpret_cast<uint4*>(sm + blk * BLK + sw128_offset(j, c16)) = o;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const float invS = 1.0f / grad_scale(dp_absmax[0]);
+
+  if (warp >= PROD_WARP0) {
+    // ------------------------------- dA loaders: [128 e x 128 j] sub-tiles -------------------------------
+    const int pt = threadIdx.x - PROD_WARP0 * 32;
+    const int c = pt & 15;          // 16-byte chunk (8 hidden units) inside the 128-unit sub-tile
+    const int row_base = pt >> 4;   // rows row_base + 16*i
+    uint32_t it = 0;
+    for (int64_t t = tile0; t < ntiles; t += tstep) {
+#pragma unroll 1
+      for (int js = 0; js < NJ; ++js, ++it) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = t * TILE_M + row_base + 16 * i;
+          v[i] = make_uint4(0, 0, 0, 0);
+          if (row < n) v[i] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + row * H + js * 128 + c * 8));
+        }
+        const uint32_t slot = it % NSTAGE;
+        mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
+        uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(stage + (c >> 3) * (TILE_M * 128) + sw128_offset(row_base + 16 * i, c & 7)) = v[i];
+        fence_proxy_async_smem();
+        mbar_arrive(full0 + 8 * slot);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, TILE_M, 128) | (1u << 16);  // B is MN-major
+      uint32_t it = 0, lt = 0;
+      for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
+        const uint32_t tb = lt & 1;
+        mbar_wait(dfempty0 + 8 * tb, ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int js = 0; js < NJ; ++js, ++it) {
+          const uint32_t slot = it % NSTAGE;
+          mbar_wait(full0 + 8 * slot, (it / NSTAGE) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int qd = 0; qd < NQ; ++qd) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t ad =
+                  umma_desc_k_sw128(a_base + slot * STAGE_BYTES + (kk >> 2) * (TILE_M * 128) + (kk & 3) * 32);
+              const uint64_t bd = umma_desc_mn_sw128(b_base + (2 * qd) * BLK + (js * 8 + kk) * 2048, BLK);
+              umma_f16(tmem_base + tb * 256 + qd * 128, ad, bd, idesc, (js | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty0 + 8 * slot);
+        }
+        umma_commit(dffull0 + 8 * tb);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------- epilogue: dF -> d_out[src], d_out[dst] -------------------------------
+    const int lg = warp & 3;
+    const int ch = warp >> 2;
+    const int r = lg * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+    uint32_t lt = 0;
+    for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
+      const uint32_t tb = lt & 1;
+      const int64_t i = t * TILE_M + r;
+      const bool live = i < n;
+      int64_t e = live ? i : n - 1;
+      if (ids) e = ids[e];
+      const int s_node = src[e], d_node = dst[e];
+      const T* xrow = tab + (int64_t)s_node * H;
+      const T* yrow = tab + (int64_t)d_node * H;
+      float* dyrow = d_out + (int64_t)d_node * H;
+      mbar_wait(dffull0 + 8 * tb, (lt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int part = 0; part < NQ * 2; ++part) {
+        const int qd = part >> 1, h16 = part & 1;
+        const int col0 = kind * CB + qd * 64 + ch * 32 + h16 * 16;   // 16 node-embedding columns
+        const uint4 xv0 = *reinterpret_cast<const uint4*>(xrow + col0);
+        const uint4 xv1 = *reinterpret_cast<const uint4*>(xrow + col0 + 8);
+        const uint4 yv0 = *reinterpret_cast<const uint4*>(yrow + col0);
+        const uint4 yv1 = *reinterpret_cast<const uint4*>(yrow + col0 + 8);
+        uint32_t f1[16], f2[16];
+        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + ch * 32 + h16 * 16, f1);
+        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + 64 + ch * 32 + h16 * 16, f2);
+        tmem_ld_wait();
+        if (part == NQ * 2 - 1) {  // all of this tile's accumulator has been read
+          tc_fence_before();
+          mbar_arrive(dfempty0 + 8 * tb);
+        }
+        const uint32_t xs[8] = {xv0.x, xv0.y, xv0.z, xv0.w, xv1.x, xv1.y, xv1.z, xv1.w};
+        const uint32_t ys[8] = {yv0.x, yv0.y, yv0.z, yv0.w, yv1.x, yv1.y, yv1.z, yv1.w};
+        float gx[16], gy[16];
+        const float sc = live ? invS : 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float2 xa = Cvt<T>::unpack(xs[m]);
+          const float2 ya = Cvt<T>::unpack(ys[m]);
+          const float a0 = __uint_as_float(f1[2 * m]) * sc, a1 = __uint_as_float(f1[2 * m + 1]) * sc;
+          const float d0 = __uint_as_float(f2[2 * m]) * sc, d1 = __uint_as_float(f2[2 * m + 1]) * sc;
+          gx[2 * m] = fmaf(a0, ya.x, d0);
+          gx[2 * m + 1] = fmaf(a1, ya.y, d1);
+          gy[2 * m] = fmaf(a0, xa.x, -d0);
+          gy[2 * m + 1] = fmaf(a1, xa.y, -d1);
+        }
+        // destination side: random rows -> 128-bit vector RED per row
+        if (live) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            red_add_v4(dyrow + col0 + 4 * k, gy[4 * k], gy[4 * k + 1], gy[4 * k + 2], gy[4 * k + 3]);
+        }
+        // source side: rows of a warp mostly share their source (edge ids ascend by source): reduce each run
+        // of equal sources across the warp first, then one coalesced RED from 16 lanes.
+        uint32_t todo = __ballot_sync(0xffffffffu, live);
+#pragma unroll 1
+        for (int iter = 0; iter < 2 && todo; ++iter) {
+          const int leader = __ffs(todo) - 1;
+          const int s_lead = __shfl_sync(0xffffffffu, s_node, leader);
+          const bool in_seg = live && s_node == s_lead && ((todo >> lane) & 1u);
+          const uint32_t seg = __ballot_sync(0xffffffffu, in_seg);
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = in_seg ? gx[k] : 0.f;
+          const float tot = warp_colsum16(v, lane);
+          if (lane < 16) atomicAdd(d_out + (int64_t)s_lead * H + col0 + lane, tot);
+          todo &= ~seg;
+        }
+        if ((todo >> lane) & 1u) {
+          float* dxrow = d_out + (int64_t)s_node * H;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            red_add_v4(dxrow + col0 + 4 * k, gx[4 * k], gx[4 * k + 1], gx[4 * k + 2], gx[4 * k + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
 // =============================================================================================
-// B2: dW1blk[BN, 2H] += dA^T . F   over all edges of this CTA's tiles
+// BW: dW1blk[BN, 2H] += dA^T . F   over all edges of this CTA's tiles
 // =============================================================================================
 template <typename T, int BN, int H>
 __global__ void __launch_bounds__(kb::THREADS, 1)
-edge_score_bwd2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-                       const int32_t* __restrict__ ids, int64_t n, const T* __restrict__ dA,
-                       const float* __restrict__ dp_absmax, float* __restrict__ dW1) {
+edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                         const int32_t* __restrict__ ids, int64_t n, const T* __restrict__ dA,
+                         const float* __restrict__ dp_absmax, float* __restrict__ dW1) {
   using namespace kb;
   using namespace tc;
   constexpr int NB = H / BN;
-  constexpr int NKB = 2 * H / 64;                 // 64-column blocks of F (N of the MMA = 2H)
   constexpr int SUB_M = 64;                       // edges per stage (K of the MMA)
-  constexpr int F_BYTES = SUB_M * 2 * H * 2;      // [64 e x 2H] as NKB blocks of [64 x 64]
+  constexpr int F_BYTES = SUB_M * 2 * H * 2;      // [64 e x 2H] as 2H/64 blocks of [64 x 64]
   constexpr int DA_BYTES = SUB_M * BN * 2;
   constexpr int STAGE = F_BYTES + DA_BYTES;
   constexpr int NSTAGE = (2 * STAGE + 4096 <= 232448) ? 2 : 1;
   constexpr int NCOLS = 2 * H;                    // TMEM columns of the accumulator
-  static_assert(NCOLS <= 512 && BN % 64 == 0, "unsupported shape");
+  static_assert(NCOLS <= 512 && BN == 128, "unsupported shape");
   constexpr int TMEM_ALLOC = NCOLS <= 128 ? 128 : (NCOLS <= 256 ? 256 : 512);
 
   extern __shared__ uint8_t smem_raw[];
@@ -532,14 +690,13 @@ edge_score_bwd2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
       mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
       uint8_t* fst = sm + slot * STAGE;
       uint8_t* dst_da = fst + F_BYTES;
-      // F: items = 64 rows x (H/8) 16-byte chunks
       for (int item = lt_id; item < SUB_M * (H / 8); item += LOAD_THREADS) {
         const int row = item / (H / 8);
         const int cc = item % (H / 8);        // chunk of 8 node-embedding columns
-        int64_t i = s * SUB_M + row;
+        const int64_t i = s * SUB_M + row;
         uint4 pr = make_uint4(0, 0, 0, 0), df = make_uint4(0, 0, 0, 0);
         if (i < n) {
-          int64_t e = ids ? ids[i] : i;
+          const int64_t e = ids ? ids[i] : i;
           const uint4 xv = *reinterpret_cast<const uint4*>(tab + (int64_t)src[e] * H + cc * 8);
           const uint4 yv = *reinterpret_cast<const uint4*>(tab + (int64_t)dst[e] * H + cc * 8);
           pr = make_uint4(Cvt<T>::mul2(xv.x, yv.x), Cvt<T>::mul2(xv.y, yv.y), Cvt<T>::mul2(xv.z, yv.z),
@@ -552,13 +709,12 @@ edge_score_bwd2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
         *reinterpret_cast<uint4*>(fst + (2 * sp) * (SUB_M * 128) + off) = pr;
         *reinterpret_cast<uint4*>(fst + (2 * sp + 1) * (SUB_M * 128) + off) = df;
       }
-      // dA: 64 rows x (BN/8) chunks of this CTA's hidden block
       for (int item = lt_id; item < SUB_M * (BN / 8); item += LOAD_THREADS) {
         const int row = item / (BN / 8);
         const int cc = item % (BN / 8);
         const int64_t i = s * SUB_M + row;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (i < n) v = *reinterpret_cast<const uint4*>(dA + i * H + nb * BN + cc * 8);
+        if (i < n) v = ld_stream_u4(reinterpret_cast<const uint4*>(dA + i * H + nb * BN + cc * 8));
         *reinterpret_cast<uint4*>(dst_da + (cc >> 3) * (SUB_M * 128) + sw128_offset(row, cc & 7)) = v;
       }
       fence_proxy_async_smem();
@@ -569,22 +725,20 @@ edge_score_bwd2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ sr
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const float invS = 1.0f / grad_scale(dp_absmax[0]);
-      const int jrow = warp * 32 + lane;   // TMEM lane == hidden unit inside the block (BN == 128) ...
-      if (BN == 128 || warp < BN / 32) {
-        float* wrow = dW1 + (int64_t)(nb * BN + jrow) * (2 * H);
+      const int jrow = warp * 32 + lane;   // TMEM lane == hidden unit inside the block
+      float* wrow = dW1 + (int64_t)(nb * BN + jrow) * (2 * H);
 #pragma unroll 1
-        for (int c0 = 0; c0 < NCOLS; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
-          tmem_ld_wait();
-          // accumulator column n: block b = n / 64 (even: product part, odd: difference part), group sp = b / 2
-          const int b = c0 >> 6;
-          const int kcol = ((b & 1) ? H : 0) + (b >> 1) * 64 + (c0 & 63);
+      for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        // accumulator column n: block b = n / 64 (even: product part, odd: difference part), group b / 2
+        const int b = c0 >> 6;
+        const int kcol = ((b & 1) ? H : 0) + (b >> 1) * 64 + (c0 & 63);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            red_add_v4(wrow + kcol + j, __uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
-                       __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS);
-        }
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(wrow + kcol + j, __uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
+                     __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS);
       }
     }
   }
@@ -603,33 +757,12 @@ size_t edge_score_bwd_tc_workspace_bytes(int64_t n, int64_t N, int64_t H) {
   return 2048 + (size_t)N * H * 2 + (size_t)n * H * 2;
 }
 
-template <typename T, int BN, int H>
-static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const int32_t* dst, const int32_t* ids,
-                          int64_t n, const float* W1, const float* b1, const float* w2, float p_drop, uint64_t seed,
-                          const float* p_fwd, const float* dp, float* d_out, float* dW1, float* db1, float* dw2,
-                          float* db2, void* ws, size_t ws_bytes, cudaStream_t st);
-
-template <typename T>
-__global__ void convert_rows_kernel_b(const float* __restrict__ in, int64_t n8, uint4* __restrict__ outp) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n8; i += stride) {
-    const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
-    const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
-    uint4 o;
-    o.x = Cvt<T>::pack_table(a.x, a.y);
-    o.y = Cvt<T>::pack_table(a.z, a.w);
-    o.z = Cvt<T>::pack_table(b.x, b.y);
-    o.w = Cvt<T>::pack_table(b.z, b.w);
-    outp[i] = o;
-  }
-}
-
-template <typename T, int BN, int H>
+template <typename T, int H>
 static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const int32_t* dst, const int32_t* ids,
                           int64_t n, const float* W1, const float* b1, const float* w2, float p_drop, uint64_t seed,
                           const float* p_fwd, const float* dp, float* d_out, float* dW1, float* db1, float* dw2,
                           float* db2, void* ws, size_t ws_bytes, cudaStream_t st) {
+  constexpr int BN = 128;
   constexpr int NB = H / BN;
   if (ws_bytes < edge_score_bwd_tc_workspace_bytes(n, N, H)) {
     set_error("sgs_edge_score_bwd: workspace too small");
@@ -648,29 +781,36 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
   g = ceil_div(n8, 256);
   convert_rows_kernel_b<T><<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(out, n8, reinterpret_cast<uint4*>(tab));
   SGS_LAUNCH_CHECK();
+  const int64_t ntiles = ceil_div(n, kb::TILE_M);
+  auto grid_for = [&](int kinds, int64_t items) {
+    int64_t gr = (int64_t)(sm_count() / kinds) * kinds;
+    if (gr > items * kinds) gr = items * kinds;
+    return (unsigned)gr;
+  };
   {
-    auto kern = edge_score_bwd1_kernel<T, BN, H>;
-    constexpr size_t used = (size_t)2 * (H / 64) * BN * 128 + 2 * kb::STAGE_BYTES + kb::TILE_M * BN * 2 + BN * 8 +
-                            16 * 8 + 16;
+    auto kern = edge_score_bwd_da_kernel<T, BN, H>;
+    constexpr size_t used = (size_t)2 * (H / 64) * BN * 128 + 3 * kb::STAGE_BYTES + BN * 8 + 16 * 8 + 16;
     const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ntiles = ceil_div(n, kb::TILE_M);
-    int64_t grid = (int64_t)(sm_count() / NB) * NB;
-    if (grid > ntiles * NB) grid = ntiles * NB;
-    kern<<<(unsigned)grid, kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp,
-                                                    absmax, d_out, dA, dw2, db1, db2);
+    kern<<<grid_for(NB, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp,
+                                                          absmax, dA, dw2, db1, db2);
     SGS_LAUNCH_CHECK();
   }
   {
-    auto kern = edge_score_bwd2_kernel<T, BN, H>;
+    auto kern = edge_score_bwd_df_kernel<T, H>;
+    constexpr size_t used = (size_t)2 * 2 * H * 128 + 3 * kb::STAGE_BYTES + 16 * 8 + 16;
+    const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
+    SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for(H / 128, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, dA, absmax, d_out);
+    SGS_LAUNCH_CHECK();
+  }
+  {
+    auto kern = edge_score_bwd_dw_kernel<T, BN, H>;
     constexpr size_t stage = (size_t)64 * 2 * H * 2 + 64 * BN * 2;
     constexpr int nstage = (2 * stage + 4096 <= 232448) ? 2 : 1;
     const size_t smem = nstage * stage + 128 + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t nsub = ceil_div(n, 64);
-    int64_t grid = (int64_t)(sm_count() / NB) * NB;
-    if (grid > nsub * NB) grid = nsub * NB;
-    kern<<<(unsigned)grid, kb::THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, dW1);
+    kern<<<grid_for(NB, ceil_div(n, 64)), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, dW1);
     SGS_LAUNCH_CHECK();
   }
   return SGS_OK;
@@ -681,20 +821,18 @@ int32_t edge_score_bwd_tc(const float* out, int64_t N, int64_t H, const int32_t*
                           float p_drop, uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
                           float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int32_t precision,
                           cudaStream_t st) {
-#define SGS_KB(T, BN, HH)                                                                                      \
-  return launch_bwd<T, BN, HH>(out, N, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, \
-                               dw2, db2, ws, ws_bytes, st)
+#define SGS_KB(T, HH)                                                                                          \
+  return launch_bwd<T, HH>(out, N, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, dw2, \
+                           db2, ws, ws_bytes, st)
   if (precision == SGS_PREC_BF16) {
-    if (H == 256) SGS_KB(__nv_bfloat16, 128, 256);
-    if (H == 128) SGS_KB(__nv_bfloat16, 128, 128);
-    if (H == 64) SGS_KB(__nv_bfloat16, 64, 64);
+    if (H == 256) SGS_KB(__nv_bfloat16, 256);
+    if (H == 128) SGS_KB(__nv_bfloat16, 128);
   } else if (precision == SGS_PREC_FP16) {
-    if (H == 256) SGS_KB(__half, 128, 256);
-    if (H == 128) SGS_KB(__half, 128, 128);
-    if (H == 64) SGS_KB(__half, 64, 64);
+    if (H == 256) SGS_KB(__half, 256);
+    if (H == 128) SGS_KB(__half, 128);
   }
 #undef SGS_KB
-  set_error("sgs_edge_score_bwd: tensor-core path supports bf16/fp16 and H in {64, 128, 256}");
+  set_error("sgs_edge_score_bwd: tensor-core path supports bf16/fp16 and H in {128, 256}");
   return SGS_E_UNSUPPORTED;
 }
 
