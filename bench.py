@@ -206,6 +206,7 @@ def run_gpu_arm(a):
     q = int(e * SAMPLE_PERC)
     model, og, oe, oa = build_model(f, c, dev, a.drop_rate)
     args = make_args(dev, a.drop_rate)
+    args.data_parallel = world > 1   # independent graph batches per rank + weight-gradient all-reduce
     crit = nn.CrossEntropyLoss()
 
     def barrier():
@@ -300,7 +301,7 @@ def run_gpu_arm(a):
                        "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
                        "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": "hybrid",
                        "conditional": True, "scorer_precision": a.precision, "gemm_precision": a.gemm_precision,
-                       "parallelism": "single" if world == 1 else f"replicas x{world}",
+                       "parallelism": "single" if world == 1 else f"dp{world}: one graph batch per rank, gate + weight-grad all-reduce (NCCL)",
                        "l2_policy": "inputs larger than L2 (graph + features >> 126 MB)",
                        "learned_wins_steps": learned},
             "epochs_per_s": world * a.steps / (ms * 1e-3), "scored_edges_per_s": world * e * a.steps / (ms * 1e-3),

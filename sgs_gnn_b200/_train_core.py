@@ -16,6 +16,7 @@ import weakref
 import torch
 import torch.nn as nn
 
+from . import dist as sdist
 from . import ops, sampling
 from .ops import SAMPLE_TRAIN
 
@@ -65,6 +66,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     g_full = ops.graph_of(batch.edge_index, n)
     tm_u8 = batch.train_mask.view(torch.uint8)
     scorer = model.edge_prob_mlp
+    dp = sdist.is_dist() and bool(getattr(args, "data_parallel", False))
     coef = args.degree_bias_coef
 
     g_rand = None
@@ -119,10 +121,13 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
         acc_l = ops.loss_forward(learned_out.detach(), batch.y, tm_u8, g_s if with_edges else None,
                                  p_s.detach() if with_edges else None)
         acc_r = ops.loss_forward(random_out.detach(), batch.y, tm_u8)
-        host = torch.cat([acc_l, acc_r, smp.state.double(), r.state.double()]).cpu()
+        gate = torch.stack([acc_l[2], acc_r[2]])
+        if dp:  # data-parallel over batches: one global decision on the summed correct-counts
+            sdist.dist.all_reduce(gate)
+        host = torch.cat([acc_l, acc_r, smp.state.double(), r.state.double(), gate]).cpu()
         _check_sampler(host[16:24], q)
         _check_sampler(host[24:32], q)
-        update_edge_mlp = bool(host[2] > host[8 + 2])
+        update_edge_mlp = bool(host[32] > host[33])
     if update_edge_mlp:
         loss = ops.fused_loss(learned_out, batch.y, tm_u8, p_s if with_edges else None, g_s if with_edges else None,
                               args.regularizer1_coef, args.consist_reg_coef, bool(args.reg1), bool(args.reg2),
@@ -174,6 +179,16 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
                 temperature = max(args.t_min, args.t_init - epoch * r_)
                 loss, update_edge_mlp = learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q,
                                                      _backward)
+                if sdist.is_dist() and bool(getattr(args, "data_parallel", False)):
+                    opts = (optimizer_edge_prob, optimizer_gnn) if update_edge_mlp else (optimizer_gnn,)
+                    seen, plist = set(), []
+                    for o in opts:
+                        for grp in o.param_groups:
+                            for prm in grp["params"]:
+                                if id(prm) not in seen:
+                                    seen.add(id(prm))
+                                    plist.append(prm)
+                    sdist.allreduce_grads(plist)
                 if update_edge_mlp:
                     conditional_update += 1
                     optimizer_edge_prob.step()

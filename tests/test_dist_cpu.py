@@ -1,0 +1,103 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (destination-range sharding, the distributed
+radix-select protocol that only moves digit histograms, gate / gradient all-reduce)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import extended as ox
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(fn, world, *args):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_destination_ranges_partition_all_edges():
+    from sgs_gnn_b200 import dist as sdist, synth
+    b = synth.make_graph("smallcora", seed=2)
+    n, e = b.num_nodes, b.num_edges
+    for world in (1, 2, 3, 8):
+        parts = [sdist.shard_by_destination(b.edge_index, n, world, r) for r in range(world)]
+        bounds = parts[0][1]
+        assert bounds[0] == 0 and bounds[-1] == n and all(bounds[i] <= bounds[i + 1] for i in range(world))
+        ids = torch.cat([p[0] for p in parts])
+        assert ids.numel() == e and torch.equal(torch.sort(ids).values, torch.arange(e))
+        for r, (idr, _) in enumerate(parts):
+            d = b.edge_index[1, idr]
+            assert bool(((d >= bounds[r]) & (d < bounds[r + 1])).all())
+            assert bool((idr[1:] > idr[:-1]).all())
+        sizes = [p[0].numel() for p in parts]
+        assert max(sizes) - min(sizes) <= e // world * 0.25 + 200      # balanced by in-degree
+
+
+def _topq_worker(rank, world, e, q, ties):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _topq_numpy import NumpyTopQOps
+    from sgs_gnn_b200 import dist as sdist
+    g = torch.Generator().manual_seed(123)
+    p = torch.rand(e, generator=g)
+    if ties:
+        p = torch.round(p * 4) / 4 + 0.25          # few distinct values -> many threshold ties
+        noise = torch.ones(e)
+    else:
+        noise = ox.exponential_noise(e, g)
+    prob = torch.softmax(torch.rand(e, generator=g), 0)
+    # contiguous id shards (rank order == edge id order)
+    lo, hi = rank * e // world, (rank + 1) * e // world
+    sel, state = sdist.DistributedTopQ(NumpyTopQOps()).select(p[lo:hi], prob[lo:hi], noise[lo:hi], q, 0, 0.3)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (sel + lo).tolist())
+    if rank == 0:
+        got = sorted(i for part in gathered for i in part)
+        S = p.sum(dtype=torch.float64).to(torch.float32)
+        want = ox.sample_topq(p, prob, q, noise, 0.3, False, S=S)
+        assert got == want.sel.tolist()
+        assert np.array([int(state[2])], dtype=np.uint32).view(np.float32)[0] == np.float32(want.tau)
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_distributed_radix_select_matches_global_topq(ties):
+    _run(_topq_worker, 2, 5000, 1200, ties)
+
+
+def _dp_worker(rank, world):
+    from sgs_gnn_b200 import dist as sdist
+    assert sdist.is_dist()
+    w = torch.nn.Parameter(torch.zeros(3))
+    v = torch.nn.Parameter(torch.zeros(2, 2))
+    u = torch.nn.Parameter(torch.zeros(1))          # no grad on any rank: must be skipped
+    w.grad = torch.full((3,), float(rank + 1))
+    v.grad = torch.full((2, 2), float(10 * (rank + 1)))
+    sdist.allreduce_grads([w, v, u])
+    assert torch.allclose(w.grad, torch.full((3,), 1.5)) and torch.allclose(v.grad, torch.full((2, 2), 15.0))
+    assert u.grad is None
+    a, b = sdist.allreduce_gate(torch.tensor(3.0 + rank), torch.tensor(5.0))
+    assert float(a) == 7.0 and float(b) == 10.0
+
+
+def test_gradient_and_gate_allreduce():
+    _run(_dp_worker, 2)

@@ -124,3 +124,46 @@ def test_module_api_matches_reference_signature(dev):
     assert mask.dtype == torch.bool and int(mask.sum()) == q and w.shape == (q,)
     assert torch.equal(mask.cpu(), _unpack(z["mask_train"], p.numel()))
     assert torch.equal(w.cpu(), t(z["weights_train"]))
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_sharded_select_steps_equal_single_select(dev, ties):
+    """The step-wise entry points (what a multi-GPU caller interleaves with histogram all-reduces),
+    driven for 3 shards inside one process: merged result == single-GPU result, bit for bit."""
+    from sgs_gnn_b200 import ops
+    from sgs_gnn_b200.dist import CudaTopQOps
+    e, q, world = 300007, 70000, 3
+    g = torch.Generator().manual_seed(9)
+    p = torch.rand(e, generator=g)
+    if ties:
+        p = torch.round(p * 8) / 8 + 0.125
+        noise = torch.ones(e)
+    else:
+        noise = ox.exponential_noise(e, g)
+    prob = torch.softmax(torch.rand(e, generator=g), 0)
+    pd, probd, nd = p.to(dev), prob.to(dev), noise.to(dev)
+    S = ops.sum_f32(pd)
+    single = ops.sample_topq(pd, probd, q, ops.SAMPLE_TRAIN, 0.3, noise=nd, S=S)
+    k = CudaTopQOps()
+    bounds = [(r * e // world) // 4 * 4 for r in range(world)] + [e]      # 16-byte aligned shard starts
+    shards = [(bounds[r], bounds[r + 1]) for r in range(world)]
+    loc = [k.keys(pd[a:b], probd[a:b], nd[a:b], ops.SAMPLE_TRAIN, 0.3, S) for a, b in shards]
+    last_local = None
+    for level in range(3):
+        if level > 0:
+            for keys, hist, state in loc:
+                k.hist(keys, hist, state, level)
+        if level == 2:
+            last_local = [h.clone() for _, h, _ in loc]
+        merged = sum(h for _, h, _ in loc)
+        for keys, hist, state in loc:
+            hist.copy_(merged)
+            k.find(hist, state, q, level)
+    tau_bin = int(loc[0][2][2].item()) & 511
+    n_eq = [int(h[tau_bin].item()) for h in last_local]
+    sels = []
+    for r, ((a, b), (keys, hist, state)) in enumerate(zip(shards, loc)):
+        sel = k.compact(keys, state, sum(n_eq[:r]), b - a)
+        sels.append(sel.long() + a)
+    got = torch.cat(sels)
+    assert torch.equal(got, single.sel.long())
