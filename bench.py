@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--workload", default="reddit")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E of the GPU workload (debug only)")
     ap.add_argument("--cpu-scale", type=float, default=1.0 / 128, help="bounded CPU sample: N, E scaled by this")
-    ap.add_argument("--precision", default=os.environ.get("SGS_SCORER_PRECISION", "fp32"),
+    ap.add_argument("--precision", default=os.environ.get("SGS_SCORER_PRECISION", "fp16"),
                     choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--gemm-precision", default=os.environ.get("SGS_GEMM_PRECISION", "fp32"),
                     choices=["fp32", "bf16", "fp16", "tf32"])
