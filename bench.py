@@ -219,19 +219,33 @@ def run_gpu_arm(a):
 
     # ---- resident arm ----
     loader = [batch]
+    # warm-up: one step with the gate off forces the learned branch, so every workspace the step can need is
+    # allocated (and cached by the allocator) before timing; then W regular steps
+    args.conditional = False
+    epoch(loader, 0)
+    args.conditional = True
     for w in range(a.warmup):
         epoch(loader, 1 + w)
     barrier()
+    profiling = bool(os.environ.get("SGS_CUDA_PROFILER"))
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
     launches0 = _lib.launch_count()
     learned = 0
     with ClockSampler(local) as clk, ops.KernelTimer() as kt:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for s in range(a.steps):
+            t_s = time.perf_counter()
             _, _, n_cond, _ = epoch(loader, 100 + s)
             learned += n_cond
+            if os.environ.get("SGS_BENCH_VERBOSE"):
+                print(f"[rank {rank}] step {s}: {1e3 * (time.perf_counter() - t_s):.1f} ms (learned={n_cond})",
+                      file=sys.stderr, flush=True)
         ev1.record()
         barrier()
+        if profiling:
+            torch.cuda.cudart().cudaProfilerStop()
         ms = ev0.elapsed_time(ev1)
         ktot = kt.totals_ms()
     launches = _lib.launch_count() - launches0
