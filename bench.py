@@ -222,7 +222,7 @@ def run_gpu_arm(a):
     # warm-up: one step with the gate off forces the learned branch, so every workspace the step can need is
     # allocated (and cached by the allocator) before timing; then W regular steps
     args.conditional = False
-    epoch(loader, 0)
+    epoch(loader, 1)   # (epoch 0 would print the reference's "[hybrid] checkpoint=..." banner to stdout)
     args.conditional = True
     for w in range(a.warmup):
         epoch(loader, 1 + w)

@@ -16,19 +16,23 @@
 // in range; it is divided out again in the epilogues.
 #include "common.cuh"
 #include "tc.cuh"
+#include "scorer_producer.cuh"
 
 namespace sgs {
 
 namespace kb {
 constexpr int TILE_M = 128;
 constexpr int STAGE_BYTES = TILE_M * 128 * 2;  // 32 KB: two [128 x 64] 16-bit blocks
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 4;
 constexpr int PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int PROD_WARP0 = EPI_WARPS + 1;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
+// the dW1 kernel has no per-tile epilogue: 16 loader warps + 1 MMA warp
+constexpr int BW_MMA_WARP = 8;
+constexpr int BW_THREADS = 17 * 32;
 }  // namespace kb
 
 // in-warp transpose-reduce: every lane holds v[0..31] (one row, 32 columns); on return lane L holds the sum over
@@ -186,60 +190,9 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 
   if (warp >= PROD_WARP0) {
     // ------------------------------- producers (as the forward) -------------------------------
-    const int pt = threadIdx.x - PROD_WARP0 * 32;
-    const int c = pt & 7;
-    const int row_base = pt >> 3;
-    uint32_t it = 0;
-    for (int64_t t = tile0; t < ntiles; t += tstep) {
-      const T* xr[4];
-      const T* yr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int64_t e = t * TILE_M + row_base + 32 * i;
-        if (e >= n) e = n - 1;
-        if (ids) e = ids[e];
-        xr[i] = tab + (int64_t)src[e] * H + c * 8;
-        yr[i] = tab + (int64_t)dst[e] * H + c * 8;
-      }
-      uint4 cx[4], cy[4], nx[4], ny[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cx[i] = *reinterpret_cast<const uint4*>(xr[i]);
-        cy[i] = *reinterpret_cast<const uint4*>(yr[i]);
-      }
-#pragma unroll
-      for (int sp = 0; sp < NSP; ++sp, ++it) {
-        if (sp + 1 < NSP) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            nx[i] = *reinterpret_cast<const uint4*>(xr[i] + (sp + 1) * 64);
-            ny[i] = *reinterpret_cast<const uint4*>(yr[i] + (sp + 1) * 64);
-          }
-        }
-        const uint32_t slot = it % NSTAGE;
-        mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
-        uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t off = sw128_offset(row_base + 32 * i, c);
-          *reinterpret_cast<uint4*>(stage + off) =
-              make_uint4(Cvt<T>::mul2(cx[i].x, cy[i].x), Cvt<T>::mul2(cx[i].y, cy[i].y),
-                         Cvt<T>::mul2(cx[i].z, cy[i].z), Cvt<T>::mul2(cx[i].w, cy[i].w));
-          *reinterpret_cast<uint4*>(stage + TILE_M * 128 + off) =
-              make_uint4(Cvt<T>::sub2(cx[i].x, cy[i].x), Cvt<T>::sub2(cx[i].y, cy[i].y),
-                         Cvt<T>::sub2(cx[i].z, cy[i].z), Cvt<T>::sub2(cx[i].w, cy[i].w));
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(full0 + 8 * slot);
-        if (sp + 1 < NSP) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            cx[i] = nx[i];
-            cy[i] = ny[i];
-          }
-        }
-      }
-    }
+    FeatureProducer<T, H, NSTAGE, STAGE_BYTES, TILE_M>::run(tab, src, dst, ids, n, tile0, tstep, ntiles,
+                                                             sm + B_BYTES, full0, empty0,
+                                                             threadIdx.x - PROD_WARP0 * 32);
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, TILE_M, BN);
@@ -271,8 +224,8 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   } else {
     // ------------------------------- epilogue: Z -> dA, parameter gradients -------------------------------
     const int lg = warp & 3;
-    const int ch = warp >> 2;
-    constexpr int CW = BN / 2;
+    constexpr int ch = 0;           // one epilogue warp per TMEM lane quarter handles all BN columns
+    constexpr int CW = BN;
     const int r = lg * 32 + lane;
     const uint32_t thr = dropout_threshold(p_drop);
     const bool drop = p_drop > 0.f;
@@ -510,7 +463,6 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   } else {
     // ------------------------------- epilogue: dF -> d_out[src], d_out[dst] -------------------------------
     const int lg = warp & 3;
-    const int ch = warp >> 2;
     const int r = lg * 32 + lane;
     const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
     uint32_t lt = 0;
@@ -527,18 +479,18 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
       mbar_wait(dffull0 + 8 * tb, (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int part = 0; part < NQ * 2; ++part) {
-        const int qd = part >> 1, h16 = part & 1;
-        const int col0 = kind * CB + qd * 64 + ch * 32 + h16 * 16;   // 16 node-embedding columns
+      for (int part = 0; part < NQ * 4; ++part) {
+        const int qd = part >> 2, q16 = part & 3;                     // 16-column slice q16 of column group qd
+        const int col0 = kind * CB + qd * 64 + q16 * 16;              // 16 node-embedding columns
         const uint4 xv0 = *reinterpret_cast<const uint4*>(xrow + col0);
         const uint4 xv1 = *reinterpret_cast<const uint4*>(xrow + col0 + 8);
         const uint4 yv0 = *reinterpret_cast<const uint4*>(yrow + col0);
         const uint4 yv1 = *reinterpret_cast<const uint4*>(yrow + col0 + 8);
         uint32_t f1[16], f2[16];
-        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + ch * 32 + h16 * 16, f1);
-        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + 64 + ch * 32 + h16 * 16, f2);
+        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + q16 * 16, f1);
+        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + 64 + q16 * 16, f2);
         tmem_ld_wait();
-        if (part == NQ * 2 - 1) {  // all of this tile's accumulator has been read
+        if (part == NQ * 4 - 1) {  // all of this tile's accumulator has been read
           tc_fence_before();
           mbar_arrive(dfempty0 + 8 * tb);
         }
@@ -601,7 +553,7 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 // BW: dW1blk[BN, 2H] += dA^T . F   over all edges of this CTA's tiles
 // =============================================================================================
 template <typename T, int BN, int H>
-__global__ void __launch_bounds__(kb::THREADS, 1)
+__global__ void __launch_bounds__(kb::BW_THREADS, 1)
 edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const T* __restrict__ dA,
                          const float* __restrict__ dp_absmax, float* __restrict__ dW1) {
@@ -637,7 +589,7 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   const int64_t nsub = (n + SUB_M - 1) / SUB_M;
   const int64_t sub0 = blockIdx.x / NB;
   const int64_t sstep = gridDim.x / NB;
-  constexpr int LOAD_THREADS = THREADS - 32;      // every warp but the MMA warp fills stages
+  constexpr int LOAD_THREADS = BW_THREADS - 32;      // every warp but the MMA warp fills stages
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -647,7 +599,7 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) {
+  if (warp == BW_MMA_WARP) {
     tmem_alloc(smem_u32(tmem_ptr_s), TMEM_ALLOC);
     tmem_relinquish();
   }
@@ -656,7 +608,7 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == MMA_WARP) {
+  if (warp == BW_MMA_WARP) {
     if (lane == 0) {
       // A = dA^T [M = BN (j) x K = 64 (e)]  MN-major;  B = F^T [N = 2H (k) x K = 64 (e)]  MN-major
       const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, BN, NCOLS > 256 ? 256 : NCOLS) | (1u << 15) | (1u << 16);
@@ -683,39 +635,65 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     __syncwarp();
   } else {
     // ---- stage fillers: F sub-tile (gather + product/difference) and the dA sub-tile from HBM ----
-    const int lt_id = threadIdx.x < MMA_WARP * 32 ? threadIdx.x : threadIdx.x - 32;  // 0 .. LOAD_THREADS-1
+    const int lt_id = threadIdx.x < BW_MMA_WARP * 32 ? threadIdx.x : threadIdx.x - 32;  // 0 .. LOAD_THREADS-1
+    constexpr int CH = H / 8;                            // 16-byte chunks per node-embedding row
+    constexpr int NIT = SUB_M * CH / LOAD_THREADS;       // F items per thread and stage
+    constexpr int NDA = SUB_M * (BN / 8) / LOAD_THREADS; // dA items per thread and stage
+    static_assert(SUB_M * CH % LOAD_THREADS == 0 && SUB_M * (BN / 8) % LOAD_THREADS == 0, "loader mapping");
     uint32_t it = 0;
     for (int64_t s = sub0; s < nsub; s += sstep, ++it) {
+      // all global loads of the stage are issued before the stage slot is waited for
+      int sn[NIT], dn[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int item = lt_id + k * LOAD_THREADS;
+        const int64_t i = s * SUB_M + item / CH;
+        sn[k] = -1;
+        dn[k] = 0;
+        if (i < n) {
+          const int64_t e = ids ? ids[i] : i;
+          sn[k] = src[e];
+          dn[k] = dst[e];
+        }
+      }
+      uint4 xv[NIT], yv[NIT], av[NDA];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int cc = (lt_id + k * LOAD_THREADS) % CH;
+        xv[k] = yv[k] = make_uint4(0, 0, 0, 0);
+        if (sn[k] >= 0) {
+          xv[k] = *reinterpret_cast<const uint4*>(tab + (int64_t)sn[k] * H + cc * 8);
+          yv[k] = *reinterpret_cast<const uint4*>(tab + (int64_t)dn[k] * H + cc * 8);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NDA; ++k) {
+        const int item = lt_id + k * LOAD_THREADS;
+        const int64_t i = s * SUB_M + item / (BN / 8);
+        av[k] = make_uint4(0, 0, 0, 0);
+        if (i < n) av[k] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + i * H + nb * BN + (item % (BN / 8)) * 8));
+      }
       const uint32_t slot = it % NSTAGE;
       mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
       uint8_t* fst = sm + slot * STAGE;
       uint8_t* dst_da = fst + F_BYTES;
-      for (int item = lt_id; item < SUB_M * (H / 8); item += LOAD_THREADS) {
-        const int row = item / (H / 8);
-        const int cc = item % (H / 8);        // chunk of 8 node-embedding columns
-        const int64_t i = s * SUB_M + row;
-        uint4 pr = make_uint4(0, 0, 0, 0), df = make_uint4(0, 0, 0, 0);
-        if (i < n) {
-          const int64_t e = ids ? ids[i] : i;
-          const uint4 xv = *reinterpret_cast<const uint4*>(tab + (int64_t)src[e] * H + cc * 8);
-          const uint4 yv = *reinterpret_cast<const uint4*>(tab + (int64_t)dst[e] * H + cc * 8);
-          pr = make_uint4(Cvt<T>::mul2(xv.x, yv.x), Cvt<T>::mul2(xv.y, yv.y), Cvt<T>::mul2(xv.z, yv.z),
-                          Cvt<T>::mul2(xv.w, yv.w));
-          df = make_uint4(Cvt<T>::sub2(xv.x, yv.x), Cvt<T>::sub2(xv.y, yv.y), Cvt<T>::sub2(xv.z, yv.z),
-                          Cvt<T>::sub2(xv.w, yv.w));
-        }
-        const int sp = cc >> 3;               // 64-column group
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int item = lt_id + k * LOAD_THREADS;
+        const int row = item / CH, cc = item % CH;
         const uint32_t off = sw128_offset(row, cc & 7);
-        *reinterpret_cast<uint4*>(fst + (2 * sp) * (SUB_M * 128) + off) = pr;
-        *reinterpret_cast<uint4*>(fst + (2 * sp + 1) * (SUB_M * 128) + off) = df;
+        *reinterpret_cast<uint4*>(fst + (2 * (cc >> 3)) * (SUB_M * 128) + off) =
+            make_uint4(Cvt<T>::mul2(xv[k].x, yv[k].x), Cvt<T>::mul2(xv[k].y, yv[k].y),
+                       Cvt<T>::mul2(xv[k].z, yv[k].z), Cvt<T>::mul2(xv[k].w, yv[k].w));
+        *reinterpret_cast<uint4*>(fst + (2 * (cc >> 3) + 1) * (SUB_M * 128) + off) =
+            make_uint4(Cvt<T>::sub2(xv[k].x, yv[k].x), Cvt<T>::sub2(xv[k].y, yv[k].y),
+                       Cvt<T>::sub2(xv[k].z, yv[k].z), Cvt<T>::sub2(xv[k].w, yv[k].w));
       }
-      for (int item = lt_id; item < SUB_M * (BN / 8); item += LOAD_THREADS) {
-        const int row = item / (BN / 8);
-        const int cc = item % (BN / 8);
-        const int64_t i = s * SUB_M + row;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (i < n) v = ld_stream_u4(reinterpret_cast<const uint4*>(dA + i * H + nb * BN + cc * 8));
-        *reinterpret_cast<uint4*>(dst_da + (cc >> 3) * (SUB_M * 128) + sw128_offset(row, cc & 7)) = v;
+#pragma unroll
+      for (int k = 0; k < NDA; ++k) {
+        const int item = lt_id + k * LOAD_THREADS;
+        const int row = item / (BN / 8), cc = item % (BN / 8);
+        *reinterpret_cast<uint4*>(dst_da + (cc >> 3) * (SUB_M * 128) + sw128_offset(row, cc & 7)) = av[k];
       }
       fence_proxy_async_smem();
       mbar_arrive(full0 + 8 * slot);
@@ -744,7 +722,7 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == BW_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_ALLOC);
   }
@@ -810,7 +788,7 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     constexpr int nstage = (2 * stage + 4096 <= 232448) ? 2 : 1;
     const size_t smem = nstage * stage + 128 + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(NB, ceil_div(n, 64)), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, dW1);
+    kern<<<grid_for(NB, ceil_div(n, 64)), kb::BW_THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, dW1);
     SGS_LAUNCH_CHECK();
   }
   return SGS_OK;

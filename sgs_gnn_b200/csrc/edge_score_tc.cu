@@ -4,9 +4,9 @@
 //
 // One persistent CTA per SM.  A CTA owns one block of BN <= 128 hidden units (its slice of W1 stays
 // resident in shared memory for the whole kernel) and walks 128-edge tiles:
-//   warps 0-7   epilogue : TMEM -> registers, +b1, ReLU, dropout, dot with w2  (2 warps per lane quarter)
-//   warp  8     MMA      : one elected thread issues tcgen05.mma / tcgen05.commit
-//   warps 9-16  producers: gather 16-bit rows of out[src], out[dst] (128-bit loads), form x*y and
+//   warps 0-3   epilogue : TMEM -> registers, +b1, ReLU, dropout, dot with w2  (one warp per TMEM lane quarter)
+//   warp  4     MMA      : one elected thread issues tcgen05.mma / tcgen05.commit
+//   warps 5-12  producers: gather 16-bit rows of out[src], out[dst] (128-bit loads), form x*y and
 //                          x-y in fp32, round once, store into the SWIZZLE_128B K-major A stage
 // Pipelines: smem stage ring (full/empty mbarriers) and a double-buffered TMEM accumulator
 // (tmem_full/tmem_empty), so gathers, MMAs and the epilogue of consecutive tiles overlap.
@@ -14,6 +14,7 @@
 // gathered 16-byte chunk of x and y feeds both blocks of the same stage.
 #include "common.cuh"
 #include "tc.cuh"
+#include "scorer_producer.cuh"
 
 namespace sgs {
 
@@ -21,11 +22,11 @@ namespace k1 {
 constexpr int TILE_M = 128;
 constexpr int STAGE_BYTES = TILE_M * 128 * 2;  // two [128 x 64] 16-bit blocks = 32 KB
 constexpr int NSTAGE = 3;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 4;
 constexpr int PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int PROD_WARP0 = EPI_WARPS + 1;
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 544
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416: at most 4 warps per SM sub-partition
 constexpr int PROD_THREADS = PROD_WARPS * 32;               // 256
 }  // namespace k1
 
@@ -157,61 +158,9 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
 
   if (warp >= PROD_WARP0) {
     // =============================== producers ===============================
-    const int pt = threadIdx.x - PROD_WARP0 * 32;
-    const int c = pt & 7;           // 16-byte chunk (8 columns) inside a 64-column block
-    const int row_base = pt >> 3;   // rows row_base + 32*i
-    uint32_t it = 0;                // running stage counter
-    for (int64_t t = tile0; t < ntiles; t += tstep) {
-      const T* xr[4];
-      const T* yr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int64_t e = t * TILE_M + row_base + 32 * i;
-        if (e >= n) e = n - 1;
-        if (ids) e = ids[e];
-        xr[i] = tab + (int64_t)src[e] * H + c * 8;
-        yr[i] = tab + (int64_t)dst[e] * H + c * 8;
-      }
-      uint4 cx[4], cy[4], nx[4], ny[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cx[i] = *reinterpret_cast<const uint4*>(xr[i]);
-        cy[i] = *reinterpret_cast<const uint4*>(yr[i]);
-      }
-#pragma unroll
-      for (int sp = 0; sp < NSP; ++sp, ++it) {
-        if (sp + 1 < NSP) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            nx[i] = *reinterpret_cast<const uint4*>(xr[i] + (sp + 1) * 64);
-            ny[i] = *reinterpret_cast<const uint4*>(yr[i] + (sp + 1) * 64);
-          }
-        }
-        const uint32_t slot = it % NSTAGE;
-        const uint32_t use = it / NSTAGE;
-        mbar_wait(empty0 + 8 * slot, (use & 1) ^ 1);
-        uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t off = sw128_offset(row_base + 32 * i, c);
-          *reinterpret_cast<uint4*>(stage + off) =
-              make_uint4(Cvt<T>::mul2(cx[i].x, cy[i].x), Cvt<T>::mul2(cx[i].y, cy[i].y),
-                         Cvt<T>::mul2(cx[i].z, cy[i].z), Cvt<T>::mul2(cx[i].w, cy[i].w));
-          *reinterpret_cast<uint4*>(stage + TILE_M * 128 + off) =
-              make_uint4(Cvt<T>::sub2(cx[i].x, cy[i].x), Cvt<T>::sub2(cx[i].y, cy[i].y),
-                         Cvt<T>::sub2(cx[i].z, cy[i].z), Cvt<T>::sub2(cx[i].w, cy[i].w));
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(full0 + 8 * slot);
-        if (sp + 1 < NSP) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            cx[i] = nx[i];
-            cy[i] = ny[i];
-          }
-        }
-      }
-    }
+    FeatureProducer<T, H, NSTAGE, STAGE_BYTES, TILE_M>::run(tab, src, dst, ids, n, tile0, tstep, ntiles,
+                                                             sm + B_BYTES, full0, empty0,
+                                                             threadIdx.x - PROD_WARP0 * 32);
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
@@ -244,9 +193,7 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
     __syncwarp();
   } else {
     // =============================== epilogue ===============================
-    const int lg = warp & 3;       // TMEM lane quarter
-    const int ch = warp >> 2;      // column half
-    constexpr int CW = BN / 2;     // columns per epilogue warp
+    const int lg = warp & 3;       // TMEM lane quarter (warps 0-3)
     const int r = lg * 32 + lane;  // row of the tile == TMEM lane
     const uint32_t thr = dropout_threshold(p_drop);
     const bool drop = p_drop > 0.f;
@@ -264,14 +211,18 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
       mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
       tc_fence_after();
       float z = 0.f;
-#pragma unroll
-      for (int c0 = 0; c0 < CW; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + ch * CW + c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
+        if (c0 + 32 >= BN) {  // accumulator drained: the MMA warp may overwrite it
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8 * acc);
+        }
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const int col = ch * CW + c0 + j4 * 4;  // column inside this CTA's hidden block
+          const int col = c0 + j4 * 4;  // column inside this CTA's hidden block
           const float4 bb = *reinterpret_cast<const float4*>(b1s + col);
           const float4 ww = *reinterpret_cast<const float4*>(w2s + col);  // already scaled by 1/(1-p)
           const float h0 = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bb.x, 0.f);
@@ -293,14 +244,7 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);  // accumulator drained: the MMA warp may overwrite it
-      // combine the two column halves of each row
-      float* zb = zsh + (lt & 1) * TILE_M;
-      if (ch == 1) zb[r] = z;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");
-      if (ch == 0 && i < n) {
-        z += zb[r];
+      if (i < n) {
         if (NB == 1) p_out[i] = 1.0f / (1.0f + expf(-(z + bias2)));
         else zpart[(int64_t)nb * n + i] = z;
       }
