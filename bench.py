@@ -337,7 +337,7 @@ def main():
     ap.add_argument("--cpu-scale", type=float, default=1.0 / 128, help="bounded CPU sample: N, E scaled by this")
     ap.add_argument("--precision", default=os.environ.get("SGS_SCORER_PRECISION", "fp16"),
                     choices=["fp32", "bf16", "fp16"])
-    ap.add_argument("--gemm-precision", default=os.environ.get("SGS_GEMM_PRECISION", "fp32"),
+    ap.add_argument("--gemm-precision", default=os.environ.get("SGS_GEMM_PRECISION", "tf32"),
                     choices=["fp32", "bf16", "fp16", "tf32"])
     ap.add_argument("--drop-rate", type=float, default=0.3)
     ap.add_argument("--no-e2e", action="store_true")

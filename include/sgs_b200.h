@@ -64,10 +64,12 @@ int32_t sgs_edge_index_gather(const int64_t* edge_index, int64_t M, const int32_
 
 size_t sgs_csr_workspace_bytes(int64_t M, int64_t N);
 /* Stable counting sort of the M edges by key (dst for the forward CSR, src for the backward
- * one): rowptr[N+1], perm[M] = edge ids in key order, nbr[M] = other[perm]. */
+ * one): rowptr[N+1], perm[M] = edge ids in key order, nbr[M] = other[perm]; optional order[N] =
+ * row ids sorted by descending degree (the SpMM / SDDMM kernels deal rows to warps in this order
+ * so that power-law hub rows start first and the tail stays balanced). */
 int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64_t N,
-                      int32_t* rowptr, int32_t* perm, int32_t* nbr, void* ws, size_t ws_bytes,
-                      sgs_stream_t stream);
+                      int32_t* rowptr, int32_t* perm, int32_t* nbr, int32_t* order, void* ws,
+                      size_t ws_bytes, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3a gcn_norm  (PyG gcn_norm + add_remaining_self_loops as called from model.py:107-111,
@@ -94,9 +96,10 @@ int32_t sgs_gcn_norm_apply(const int32_t* rowptr, const int32_t* perm, const int
 #define SGS_SPMM_RELU 1
 #define SGS_SPMM_DROPOUT 2
 #define SGS_SPMM_ACCUM 4
-int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, const float* dis,
-                 const float* loopw, const float* h, int64_t N, int64_t D, const float* bias,
-                 float* out, int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream);
+int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what,
+                 const int32_t* order /* may be NULL */, const float* dis, const float* loopw,
+                 const float* h, int64_t N, int64_t D, const float* bias, float* out, int32_t flags,
+                 float p_drop, uint64_t seed, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3c backward helpers (autograd of GCNConv, training_hybrid.py:135)
@@ -111,7 +114,8 @@ int32_t sgs_colsum(const float* G, int64_t N, int64_t D, float* colsum, sgs_stre
  * tmp_g[M], tmp_t[M], tmp_a[N] are scratch.  dw[M] in original edge order; accumulate != 0
  * adds to dw (both GCN layers share one edge_weight). */
 int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
-                          const float* what_dst, const int32_t* rowptr_src, const int32_t* perm_src,
+                          const float* what_dst, const int32_t* order_dst /* may be NULL */,
+                          const int32_t* rowptr_src, const int32_t* perm_src,
                           const int32_t* src, const int32_t* dst, const float* G, const float* h,
                           const float* dis, const float* deg, const float* loopw, int64_t M,
                           int64_t N, int64_t D, float* tmp_g, float* tmp_t, float* tmp_a, float* dw,

@@ -78,15 +78,17 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
             const float* __restrict__ what, const float* __restrict__ dis,
             const float* __restrict__ loopw, const float* __restrict__ h, int64_t N, int D,
             const float* __restrict__ bias, float* __restrict__ out, int flags, float p_drop,
-            uint64_t seed) {
+            uint64_t seed, const int32_t* __restrict__ order) {
   const int lane = threadIdx.x & 31;
   const int col0 = blockIdx.y * (32 * VEC * K);
-  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int64_t idx = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
   const uint32_t thr = dropout_threshold(p_drop);
   const float scale = (flags & SGS_SPMM_DROPOUT) ? 1.0f / (1.0f - p_drop) : 1.0f;
 
-  for (; row < N; row += step) {
+  // `order` lists the rows heaviest-first; dealing them round-robin to the warps balances the power-law tail
+  for (; idx < N; idx += step) {
+    const int64_t row = order ? order[idx] : idx;
     float acc[K][VEC];
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -188,11 +190,13 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
                        const int32_t* __restrict__ nbr, const float* __restrict__ what,
                        const float* __restrict__ G, const float* __restrict__ h,
                        const float* __restrict__ dis, const float* __restrict__ loopw, int64_t N, int D,
-                       float* __restrict__ tmp_g, float* __restrict__ tmp_t, float* __restrict__ tmp_a) {
+                       float* __restrict__ tmp_g, float* __restrict__ tmp_t, float* __restrict__ tmp_a,
+                       const int32_t* __restrict__ order) {
   const int lane = threadIdx.x & 31;
-  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int64_t idx = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (; row < N; row += step) {
+  for (; idx < N; idx += step) {
+    const int64_t row = order ? order[idx] : idx;
     float g_row[K][VEC];
     const float* gr = G + row * D;
 #pragma unroll
@@ -201,7 +205,7 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 #pragma unroll
       for (int t = 0; t < VEC; ++t) g_row[k][t] = (c + t < D) ? gr[c + t] : 0.f;
     }
-    auto dot_with = [&](const float* hp) {
+    auto partial_dot = [&](const float* hp) {
       float d = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
@@ -218,13 +222,36 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           }
         }
       }
-      return warp_sum(d);
+      return d;
     };
+    auto dot_with = [&](const float* hp) { return warp_sum(partial_dot(hp)); };
     const int beg = rowptr[row], end = rowptr[row + 1];
     float tsum = 0.f;
-    for (int i = beg; i < end; ++i) {
-      const int s = nbr[i];
-      const float g = dot_with(h + (int64_t)s * D);
+    // four neighbours per iteration: their row loads and shuffle reductions are independent (ILP)
+    int i = beg;
+    for (; i + 4 <= end; i += 4) {
+      float d0 = partial_dot(h + (int64_t)nbr[i] * D);
+      float d1 = partial_dot(h + (int64_t)nbr[i + 1] * D);
+      float d2 = partial_dot(h + (int64_t)nbr[i + 2] * D);
+      float d3 = partial_dot(h + (int64_t)nbr[i + 3] * D);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+      }
+      if (lane < 4) {
+        const float g = lane == 0 ? d0 : (lane == 1 ? d1 : (lane == 2 ? d2 : d3));
+        const int e = perm[i + lane];
+        const float t = g * what[i + lane];
+        tmp_g[e] = g;
+        tmp_t[e] = t;
+        tsum += t;
+      }
+    }
+    for (; i < end; ++i) {
+      const float g = dot_with(h + (int64_t)nbr[i] * D);
       if (lane == 0) {
         const int e = perm[i];
         const float t = g * what[i];
@@ -233,6 +260,8 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
         tsum += t;
       }
     }
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
     const float gl = dot_with(h + row * D);
     if (lane == 0) {
       const float d = dis[row];
@@ -310,7 +339,7 @@ int32_t sgs_gcn_norm_apply(const int32_t* rowptr, const int32_t* perm, const int
   return SGS_OK;
 }
 
-int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, const float* dis,
+int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order, const float* dis,
                  const float* loopw, const float* h, int64_t N, int64_t D, const float* bias, float* out,
                  int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream) {
   SGS_CHECK_ARG(N > 0 && D > 0 && D < (1 << 20), "bad sizes");
@@ -324,7 +353,7 @@ int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, c
   do {                                                                                                 \
     dim3 grid(row_grid(N), (unsigned)ceil_div(D, 32 * VEC * K));                                       \
     spmm_kernel<VEC, K><<<grid, block, 0, st>>>(rowptr, nbr, what, dis, loopw, h, N, (int)D, bias, out, \
-                                                flags, p_drop, seed);                                  \
+                                                flags, p_drop, seed, order);                           \
   } while (0)
   if (vec4) {
     if (D <= 128) SGS_SPMM_LAUNCH(4, 1);
@@ -365,7 +394,8 @@ int32_t sgs_colsum(const float* G, int64_t N, int64_t D, float* colsum, sgs_stre
 }
 
 int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
-                          const float* what_dst, const int32_t* rowptr_src, const int32_t* perm_src,
+                          const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
+                          const int32_t* perm_src,
                           const int32_t* src, const int32_t* dst, const float* G, const float* h,
                           const float* dis, const float* deg, const float* loopw, int64_t M, int64_t N,
                           int64_t D, float* tmp_g, float* tmp_t, float* tmp_a, float* dw, int32_t accumulate,
@@ -380,7 +410,7 @@ int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, co
 #define SGS_SDDMM_LAUNCH(VEC, K)                                                                         \
   edge_grad_sddmm_kernel<VEC, K><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, \
                                                                  G, h, dis, loopw, N, (int)D, tmp_g, tmp_t, \
-                                                                 tmp_a)
+                                                                 tmp_a, order_dst)
   if (vec4 && D <= 128) SGS_SDDMM_LAUNCH(4, 1);
   else if (vec4 && D <= 256) SGS_SDDMM_LAUNCH(4, 2);
   else if (vec4 && D <= 512) SGS_SDDMM_LAUNCH(4, 4);

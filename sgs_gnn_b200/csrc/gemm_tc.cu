@@ -1,11 +1,214 @@
-// K4 tensor-core path (tcgen05 + TMA).  Placeholder until the kernel lands: reports
-// SGS_E_UNSUPPORTED so callers fail loudly instead of silently changing precision.
+// K4 tensor-core path: C[M,N] (+)= A[M,K] . B[N,K]^T on tcgen05 (kind::tf32 on the fp32 operands as they
+// lie in HBM), operands streamed by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 6-stage mbarrier ring,
+// fp32 accumulators double-buffered in TMEM, persistent CTAs over 128x128 output tiles.
+//   warp 0: TMA producer (one elected thread)      warp 1: MMA issuer (one thread) + TMEM allocation
+//   warps 2-5: epilogue (TMEM -> registers -> global, one warp per TMEM lane quarter)
+// K and N tails come for free from TMA's out-of-bounds zero fill; M/N tails are masked in the epilogue.
+// Requirements (checked, SGS_E_UNSUPPORTED otherwise): unit stride along K, row strides multiples of 4
+// elements (16 B) and 16-byte aligned bases -- the Python wrapper pads odd strides once (e.g. F = 602).
+#include <cuda.h>
+
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace sgs {
-int32_t gemm_tc(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
-                int32_t, int32_t, cudaStream_t) {
-  set_error("sgs_gemm: tensor-core path not built yet");
-  return SGS_E_UNSUPPORTED;
+
+namespace k4 {
+constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 B rows
+constexpr int STAGE_BYTES = (BM + BN) * BK * 4;     // 32 KB
+constexpr int NSTAGE = 6;
+constexpr int THREADS = 6 * 32;
+}  // namespace k4
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
 }
+
+// 2-D fp32 tensor [rows, K] with row stride ld (elements); box = [128 rows x 32 K], 128-byte swizzle
+static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t K, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)k4::BK, (cuuint32_t)k4::BM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(k4::THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 float* __restrict__ C, int64_t ldc, int M, int N, int K, int accumulate) {
+  using namespace k4;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* sm = smem_raw + pad;
+  const uint32_t sm_addr = raw_addr + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + NSTAGE * STAGE_BYTES);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * NSTAGE, tfull0 = empty0 + 8 * NSTAGE,
+                 tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int ntiles = tiles_m * tiles_n;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4 * 32);
+    }
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_s), 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // consecutive CTAs walk down M inside one N tile: the B tile stays hot in L2
+        const int tm = t % tiles_m, tn = t / tiles_m;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t slot = it % NSTAGE;
+          mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(full0 + 8 * slot, STAGE_BYTES);
+          const uint32_t dst = sm_addr + slot * STAGE_BYTES;
+          tma_load_2d(dst, &map_a, full0 + 8 * slot, kb * BK, tm * BM);
+          tma_load_2d(dst + BM * BK * 4, &map_b, full0 + 8 * slot, kb * BK, tn * BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(2 /* TF32 */, BM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1;
+        mbar_wait(tempty0 + 8 * acc, ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t slot = it % NSTAGE;
+          mbar_wait(full0 + 8 * slot, (it / NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = sm_addr + slot * STAGE_BYTES;
+          const uint32_t b_addr = a_addr + BM * BK * 4;
+#pragma unroll
+          for (int k8 = 0; k8 < BK / 8; ++k8)
+            umma_tf32(tmem_base + acc * BN, umma_desc_k_sw128(a_addr + k8 * 32), umma_desc_k_sw128(b_addr + k8 * 32),
+                      idesc, (kb | k8) != 0 ? 1u : 0u);
+          umma_commit(empty0 + 8 * slot);
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lg = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const uint32_t acc = lt & 1;
+      const int tm = t % tiles_m, tn = t / tiles_m;
+      const int row = tm * BM + lg * 32 + lane;
+      mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8 * acc);
+        }
+        const int col = tn * BN + c0;
+        if (row < M && col < N) {
+          float* cp = C + (int64_t)row * ldc + col;
+          if (col + 32 <= N && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (accumulate) {
+                const float4 p = *reinterpret_cast<const float4*>(cp + j);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              *reinterpret_cast<float4*>(cp + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < N) cp[j] = accumulate ? cp[j] + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+int32_t gemm_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                int64_t N, int64_t K, int32_t accumulate, int32_t precision, cudaStream_t st) {
+  if (precision != SGS_PREC_TF32) {
+    set_error("sgs_gemm: the tensor-core GEMM runs kind::tf32 on fp32 operands (precision SGS_PREC_TF32)");
+    return SGS_E_UNSUPPORTED;
+  }
+  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {
+    set_error("sgs_gemm: TMA needs 16-byte aligned operand bases and row strides (lda, ldb multiples of 4)");
+    return SGS_E_UNSUPPORTED;
+  }
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, A, M, K, lda) || !make_map(&mb, B, N, K, ldb)) {
+    set_error("sgs_gemm: cuTensorMapEncodeTiled failed");
+    return SGS_E_CUDA;
+  }
+  const size_t smem = (size_t)k4::NSTAGE * k4::STAGE_BYTES + 256 + 1024;
+  SGS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = ceil_div(M, k4::BM) * ceil_div(N, k4::BN);
+  const int64_t grid = ntiles < sm_count() ? ntiles : sm_count();
+  gemm_tf32_kernel<<<(unsigned)grid, k4::THREADS, smem, st>>>(ma, mb, C, ldc, (int)M, (int)N, (int)K, accumulate);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
 }  // namespace sgs

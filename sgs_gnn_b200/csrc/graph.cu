@@ -78,6 +78,16 @@ static inline int grid_for(int64_t n, int block, int waves = 8) {
 
 static size_t cub_temp_bound(int64_t M) { return (size_t)(32u << 20) + (size_t)(M / 8) * 4; }
 
+// keys for the degree sort: ~degree so that an ascending radix sort yields heaviest rows first
+__global__ void degree_keys_kernel(const int32_t* __restrict__ rowptr, int64_t N, uint32_t* __restrict__ keys,
+                                   int32_t* __restrict__ ids) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    keys[i] = ~(uint32_t)(rowptr[i + 1] - rowptr[i]);
+    ids[i] = (int32_t)i;
+  }
+}
+
 }  // namespace sgs
 
 using namespace sgs;
@@ -107,25 +117,51 @@ int32_t sgs_edge_index_gather(const int64_t* edge_index, int64_t M, const int32_
 }
 
 size_t sgs_csr_workspace_bytes(int64_t M, int64_t N) {
-  (void)N;
-  size_t m = (size_t)(M > 0 ? M : 1);
-  return 4 * m * sizeof(int32_t) + 1024 + cub_temp_bound(M);
+  size_t m = (size_t)(M > N ? M : N);
+  if (m < 1) m = 1;
+  return 4 * m * sizeof(int32_t) + 1024 + cub_temp_bound((int64_t)m);
+}
+
+static int32_t degree_order(const int32_t* rowptr, int64_t N, int32_t* order, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
+  uint32_t* kA = (uint32_t*)ws;
+  uint32_t* kB = kA + N;
+  int32_t* vA = (int32_t*)(kB + N);
+  int32_t* vB = vA + N;
+  char* temp = (char*)(((uintptr_t)(vB + N) + 255) & ~(uintptr_t)255);
+  size_t temp_avail = ws_bytes - (size_t)(temp - (char*)ws);
+  degree_keys_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(rowptr, N, kA, vA);
+  SGS_LAUNCH_CHECK();
+  cub::DoubleBuffer<uint32_t> dk(kA, kB);
+  cub::DoubleBuffer<int32_t> dv(vA, vB);
+  size_t need = 0;
+  SGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)N, 0, 32, st));
+  if (need > temp_avail) {
+    set_error("sgs_csr_build: cub temp %zu > available %zu", need, temp_avail);
+    return SGS_E_WORKSPACE;
+  }
+  SGS_CUDA(cub::DeviceRadixSort::SortPairs(temp, need, dk, dv, (int)N, 0, 32, st));
+  count_launch(4);
+  SGS_CUDA(cudaMemcpyAsync(order, dv.Current(), N * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return SGS_OK;
 }
 
 int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64_t N, int32_t* rowptr,
-                      int32_t* perm, int32_t* nbr, void* ws, size_t ws_bytes, sgs_stream_t stream) {
+                      int32_t* perm, int32_t* nbr, int32_t* order, void* ws, size_t ws_bytes,
+                      sgs_stream_t stream) {
   SGS_CHECK_ARG(M >= 0 && N > 0, "bad sizes");
   SGS_CHECK_ARG(rowptr != nullptr, "null rowptr");
   cudaStream_t st = as_stream(stream);
-  if (M == 0) {
-    SGS_CUDA(cudaMemsetAsync(rowptr, 0, (N + 1) * sizeof(int32_t), st));
-    return SGS_OK;
-  }
-  SGS_CHECK_ARG(key && other && perm && nbr && ws, "null pointer");
-  if (ws_bytes < sgs_csr_workspace_bytes(M, N)) {
+  if (ws_bytes < sgs_csr_workspace_bytes(M, N) || !ws) {
     set_error("sgs_csr_build: workspace too small");
     return SGS_E_WORKSPACE;
   }
+  if (M == 0) {
+    SGS_CUDA(cudaMemsetAsync(rowptr, 0, (N + 1) * sizeof(int32_t), st));
+    if (order) return degree_order(rowptr, N, order, ws, ws_bytes, st);
+    return SGS_OK;
+  }
+  SGS_CHECK_ARG(key && other && perm && nbr, "null pointer");
   int32_t* kA = (int32_t*)ws;
   int32_t* kB = kA + M;
   int32_t* vA = kB + M;
@@ -152,6 +188,7 @@ int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64
   SGS_CUDA(cudaMemcpyAsync(perm, dv.Current(), M * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   gather_i32_kernel<<<grid_for(M, 256), 256, 0, st>>>(other, dv.Current(), M, nbr);
   SGS_LAUNCH_CHECK();
+  if (order) return degree_order(rowptr, N, order, ws, ws_bytes, st);
   return SGS_OK;
 }
 }

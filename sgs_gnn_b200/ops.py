@@ -130,7 +130,7 @@ class GcnNorm:
     def __init__(self, graph, w):
         dev = graph.device
         n, m = graph.num_nodes, graph.num_edges
-        rowptr, perm, nbr = graph.csr_dst
+        rowptr, perm, nbr, _ = graph.csr_dst
         self.deg = torch.empty(n, dtype=torch.float32, device=dev)
         self.dis = torch.empty_like(self.deg)
         self.loopw = torch.empty_like(self.deg)
@@ -145,7 +145,7 @@ class GcnNorm:
     def what_src(self):
         if self._what_src is None:
             g = self._graph
-            rowptr, perm, nbr = g.csr_src
+            rowptr, perm, nbr, _ = g.csr_src
             self._what_src = torch.empty(max(g.num_edges, 1), dtype=torch.float32, device=g.device)
             check(lib().sgs_gcn_norm_apply(_p(rowptr), _p(perm), _p(nbr), _p(self._w), _p(self.dis),
                                            g.num_edges, g.num_nodes, _p(self._what_src), _stream()),
@@ -205,12 +205,13 @@ class Graph:
         rowptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
         perm = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
         nbr = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
+        order = torch.empty(n, dtype=torch.int32, device=self.device)
         nbytes = lib().sgs_csr_workspace_bytes(m, n)
         ws = _ws(nbytes, self.device)
         with _timed("csr_build"):
-            check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(ws), ws.numel(),
-                                      _stream()), "sgs_csr_build")
-        return rowptr, perm, nbr
+            check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(order), _p(ws),
+                                      ws.numel(), _stream()), "sgs_csr_build")
+        return rowptr, perm, nbr, order
 
     @property
     def csr_dst(self):
@@ -277,21 +278,52 @@ def gemm(a, a_sm, a_sk, b, b_sn, b_sk, m, n, k, out=None, accumulate=False, prec
     return out
 
 
-def linear_nt(x, w, precision=None):
+_pad_cache = {}
+
+
+def _rows_aligned16(t, cache=False):
+    """TMA needs 16-byte aligned row strides: returns (tensor, ld) with ld % 4 == 0, copying into a padded
+    buffer when the row length is odd (e.g. F = 602).  Static inputs (node features) are padded once."""
+    k = t.size(1)
+    if k % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t, k
+    if cache:
+        key = id(t)
+        hit = _pad_cache.get(key)
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2], hit[2].size(1)
+    ld = (k + 3) // 4 * 4
+    buf = torch.zeros(t.size(0), ld, dtype=t.dtype, device=t.device)
+    buf[:, :k].copy_(t)
+    if cache:
+        try:
+            _pad_cache[key] = (weakref.ref(t, lambda _r, kk=key, c=_pad_cache: c.pop(kk, None)), t._version, buf)
+        except TypeError:
+            pass
+    return buf, ld
+
+
+def linear_nt(x, w, precision=None, static_x=False):
     """x[M,K] @ w[N,K]^T"""
     x = _req(x, torch.float32, "x")
     w = _req(w, torch.float32, "weight")
-    return gemm(x, x.size(1), 1, w, w.size(1), 1, x.size(0), w.size(0), x.size(1), precision=precision)
+    prec = _state["gemm"] if precision is None else precision
+    m, k, n = x.size(0), x.size(1), w.size(0)
+    if prec == PREC_TF32:
+        xa, lda = _rows_aligned16(x, cache=static_x)
+        wa, ldb = _rows_aligned16(w)
+        return gemm(xa, lda, 1, wa, ldb, 1, m, n, k, precision=prec)
+    return gemm(x, k, 1, w, k, 1, m, n, k, precision=prec)
 
 
 def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False):
-    rowptr, _perm, nbr = csr
+    rowptr, _perm, nbr, order = csr
     n, d = h.shape
     if out is None:
         out = torch.empty(n, d, dtype=torch.float32, device=h.device)
     flags = (SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0)
     with _timed(f"spmm_d{d}"):
-        check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(norm.dis) if norm is not None else None,
+        check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(order), _p(norm.dis) if norm is not None else None,
                              _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
                              float(p_drop), int(seed), _stream()), "sgs_spmm")
     return out
@@ -310,7 +342,7 @@ class GCNConvFn(torch.autograd.Function):
         if x.size(0) != graph.num_nodes:
             raise RuntimeError("x must have one row per node")
         norm = graph.norm(edge_weight)
-        h = linear_nt(x, weight)
+        h = linear_nt(x, weight, static_x=not x.requires_grad)
         out = spmm(graph.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed)
         ctx.graph, ctx.norm, ctx.relu, ctx.p_drop = graph, norm, relu, p_drop
         ctx.has_w = edge_weight is not None
@@ -337,18 +369,20 @@ class GCNConvFn(torch.autograd.Function):
         if need_w or need_x:
             dh = spmm(graph.csr_src, norm.what_src, norm, g)
             fin = x.size(1)
+            # reductions over the node dimension stay on the fp32 split-K path (MN-major operands)
             if need_w:  # dW[d, fin] = dh^T x
-                dw = gemm(dh, 1, d, x, 1, fin, d, fin, n)
+                dw = gemm(dh, 1, d, x, 1, fin, d, fin, n, precision=PREC_FP32)
             if need_x:  # dx[n, fin] = dh W
-                dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d)
+                dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d, precision=PREC_FP32)
         if need_ew and ctx.has_w:
             m = graph.num_edges
             dew = torch.empty(m, dtype=torch.float32, device=g.device)
             tmp = torch.empty(2 * m + n, dtype=torch.float32, device=g.device)
-            rp_d, pm_d, nb_d = graph.csr_dst
-            rp_s, pm_s, _ = graph.csr_src
+            rp_d, pm_d, nb_d, od_d = graph.csr_dst
+            rp_s, pm_s, _, _ = graph.csr_src
             with _timed(f"edge_grad_d{d}"):
-                check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(rp_s), _p(pm_s),
+                check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(od_d), _p(rp_s),
+                                              _p(pm_s),
                                               _p(graph.src), _p(graph.dst), _p(g), _p(h), _p(norm.dis),
                                               _p(norm.deg), _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]),
                                               _p(tmp[2 * m:]), _p(dew), 0, _stream()), "sgs_gcn_edge_grad")

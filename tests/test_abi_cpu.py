@@ -59,7 +59,7 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert h.sgs_gemm(None, 1, 1, None, 1, 1, None, 4, 4, 4, 4, 0, 0, None) == -1
     assert b"null pointer" in h.sgs_last_error()
     assert h.sgs_topq_find(None, None, 1, 0, None) == -1
-    assert h.sgs_spmm(None, None, None, None, None, None, 0, 4, None, None, 0, 0.0, 0, None) == -1
+    assert h.sgs_spmm(None, None, None, None, None, None, None, 0, 4, None, None, 0, 0.0, 0, None) == -1
 
 
 def test_ops_refuse_cpu_tensors():

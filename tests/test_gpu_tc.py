@@ -125,3 +125,18 @@ def test_scorer_tc_backward(dev, prec, h, e, subset, p_drop):
     for name, a, r, em in zip(("d_out", "dW1", "db1", "dw2", "db2"), grads[prec], grads["fp32"], emul):
         assert _l2rel(a, em) <= L2BOUND_VS_EMUL[prec], ("vs emulation", name, prec, h, e, _l2rel(a, em))
         assert _l2rel(a, r) <= L2BOUND_VS_FP32[prec], ("vs fp32 path", name, prec, h, e, _l2rel(a, r))
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (1000, 256, 602), (333, 41, 256), (5000, 256, 256), (129, 7, 33)])
+def test_gemm_tf32_tma(dev, m, n, k):
+    """K4 tensor-core GEMM (tcgen05 kind::tf32 + TMA).  Stated bound for tf32 operands: 2e-3 of max |C|."""
+    from sgs_gnn_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    want = (a.double() @ b.double().t()).float()
+    got = ops.linear_nt(a.to(dev), b.to(dev), precision=ops.PREC_TF32).cpu()
+    err = float((got - want).abs().max() / want.abs().max())
+    assert got.shape == (m, n) and err < 2e-3, err
+    ref32 = ops.linear_nt(a.to(dev), b.to(dev), precision=ops.PREC_FP32).cpu()
+    assert float((ref32 - want).abs().max() / want.abs().max()) < 1e-5
