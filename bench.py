@@ -200,13 +200,24 @@ def run_gpu_arm(a):
     ops.set_precision(gemm=a.gemm_precision, scorer=a.precision)
     _lib.lib()
 
-    # weak scaling: every rank trains on its own replica graph (seed differs per rank)
-    batch = synth.make_graph(a.workload, seed=42 + rank, device=dev, scale=a.scale)
-    n, e, f, c = batch.num_nodes, batch.num_edges, batch.x.size(1), batch.num_classes
+    shard = world > 1 and a.parallel == "shard"
+    if shard:
+        # ONE graph, edges sharded by destination-node range over the ranks (strong scaling)
+        from sgs_gnn_b200 import sharded
+        full = synth.make_graph(a.workload, seed=42, device=dev, scale=a.scale)
+        n, e, f, c = full.num_nodes, full.num_edges, full.x.size(1), full.num_classes
+        batch = sharded.ShardedBatch(full, sharded.Comm())
+        del full
+        torch.cuda.empty_cache()
+    else:
+        # weak scaling: every rank trains on its own replica graph (seed differs per rank)
+        batch = synth.make_graph(a.workload, seed=42 + rank, device=dev, scale=a.scale)
+        n, e, f, c = batch.num_nodes, batch.num_edges, batch.x.size(1), batch.num_classes
     q = int(e * SAMPLE_PERC)
+    units = 1 if shard else world     # graphs processed per step over all ranks
     model, og, oe, oa = build_model(f, c, dev, a.drop_rate)
     args = make_args(dev, a.drop_rate)
-    args.data_parallel = world > 1   # independent graph batches per rank + weight-gradient all-reduce
+    args.data_parallel = world > 1 and not shard   # independent graph batches per rank + weight-gradient all-reduce
     crit = nn.CrossEntropyLoss()
 
     def barrier():
@@ -254,7 +265,7 @@ def run_gpu_arm(a):
         tms = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    value = world * q * a.steps / (ms * 1e-3)
+    value = units * q * a.steps / (ms * 1e-3)
 
     # ---- e2e arm: batch lives in pinned host memory, uploaded inside train() every step ----
     e2e = None
@@ -277,7 +288,7 @@ def run_gpu_arm(a):
             tms = torch.tensor([ms_e], device=dev, dtype=torch.float64)
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             ms_e = float(tms.item())
-        e2e = {"value": world * q * a.steps / (ms_e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
+        e2e = {"value": units * q * a.steps / (ms_e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 32 * 8 + 4, "ms_per_step": ms_e / a.steps}
         del host, loader_h
 
@@ -292,13 +303,14 @@ def run_gpu_arm(a):
     flops_per_edge = 2 * (2 * HIDDEN) * HIDDEN + 2 * HIDDEN          # SURVEY 8(d)-bis K1 (concat form)
     # one timed call scores all E edges (the hybrid backward's recompute is in edge_score_bwd)
     k1_avg_s = (k1_ms / max(k1_n, 1)) * 1e-3
-    achieved = e * flops_per_edge / k1_avg_s / 1e12 if k1_avg_s > 0 else 0.0
+    e_k1 = batch.edge_index.size(1)   # edges one K1 launch scores on this rank (the local shard when sharded)
+    achieved = e_k1 * flops_per_edge / k1_avg_s / 1e12 if k1_avg_s > 0 else 0.0
     roofline = {"kernel": "sgs_edge_score_fwd (K1, all E edges)", "bound": "tensor", "achieved": achieved,
                 "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
                 "peak_source": f"{pk['src']} bf16 sustained", "launches_timed": k1_n,
                 "avg_launch_ms": k1_ms / max(k1_n, 1),
-                "hbm_view": {"algorithmic_bytes": e * 1032 + n * 1028,
-                             "achieved_gbs": (e * 1032 + n * 1028) / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0,
+                "hbm_view": {"algorithmic_bytes": e_k1 * 1032 + n * 1028,
+                             "achieved_gbs": (e_k1 * 1032 + n * 1028) / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0,
                              "peak_gbs": pk["hbm"]}}
     shares = {k: round(v[0] / ms, 4) for k, v in sorted(ktot.items(), key=lambda kv: -kv[1][0])}
 
@@ -308,17 +320,22 @@ def run_gpu_arm(a):
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": "sampled_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32"}.get(a.precision, a.precision), "data": "synthetic",
             "config": {"workload": f"{a.workload}-shape hybrid epoch, single full-graph batch" +
                                    ("" if a.scale == 1.0 else f" (scaled {a.scale:g}x)"),
                        "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
                        "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": "hybrid",
                        "conditional": True, "scorer_precision": a.precision, "gemm_precision": a.gemm_precision,
-                       "parallelism": "single" if world == 1 else f"dp{world}: one graph batch per rank, gate + weight-grad all-reduce (NCCL)",
+                       "parallelism": "single" if world == 1 else (
+                           f"shard{world}: one graph, edges sharded by destination-node range; distributed radix "
+                           "top-q (digit-histogram all-reduce), slab all-gather / reduce-scatter, partial weight-grad "
+                           "all-reduce (NCCL)" if shard else
+                           f"dp{world}: one graph batch per rank, gate + weight-grad all-reduce (NCCL)"),
                        "l2_policy": "inputs larger than L2 (graph + features >> 126 MB)",
                        "learned_wins_steps": learned},
-            "epochs_per_s": world * a.steps / (ms * 1e-3), "scored_edges_per_s": world * e * a.steps / (ms * 1e-3),
+            "epochs_per_s": units * a.steps / (ms * 1e-3), "scored_edges_per_s": units * e * a.steps / (ms * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernel_time_share": shares, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
@@ -340,6 +357,8 @@ def main():
     ap.add_argument("--gemm-precision", default=os.environ.get("SGS_GEMM_PRECISION", "tf32"),
                     choices=["fp32", "bf16", "fp16", "tf32"])
     ap.add_argument("--drop-rate", type=float, default=0.3)
+    ap.add_argument("--parallel", default=os.environ.get("SGS_PARALLEL", "shard"), choices=["shard", "dp"],
+                    help="N > 1: shard ONE graph by destination range (strong scaling) or one graph per rank (weak)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

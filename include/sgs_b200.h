@@ -120,6 +120,18 @@ int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, co
                           const float* dis, const float* deg, const float* loopw, int64_t M,
                           int64_t N, int64_t D, float* tmp_g, float* tmp_t, float* tmp_a, float* dw,
                           int32_t accumulate, sgs_stream_t stream);
+/* The same computation in two phases for a caller whose edges are sharded by destination across
+ * GPUs: _partial runs the SDDMM and the per-node sums over the local edges (G must be
+ * zero outside the owned rows), the caller all-reduces tmp_a[N], _final applies the formula. */
+int32_t sgs_gcn_edge_grad_partial(const int32_t* rowptr_dst, const int32_t* perm_dst,
+                                  const int32_t* nbr_dst, const float* what_dst,
+                                  const int32_t* order_dst /* may be NULL */, const int32_t* rowptr_src,
+                                  const int32_t* perm_src, const float* G, const float* h,
+                                  const float* dis, const float* loopw, int64_t M, int64_t N, int64_t D,
+                                  float* tmp_g, float* tmp_t, float* tmp_a, sgs_stream_t stream);
+int32_t sgs_gcn_edge_grad_final(const int32_t* src, const int32_t* dst, const float* tmp_g,
+                                const float* tmp_a, const float* dis, const float* deg, int64_t M,
+                                float* dw, int32_t accumulate, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 dense contraction  C[M,N] (+)= A[M,K] . B[N,K]^T with arbitrary element strides
@@ -221,9 +233,12 @@ int32_t sgs_scatter_selected(const float* src, const int32_t* sel, int64_t q, fl
  *   CE over train rows + c1*[sum_label>1]*BCE(p_s, same-class label) over sampled edges with
  *   both endpoints in the train mask + c2*MSE(p_s, cos(logits[src], logits[dst])).
  * acc: device double[8] = {ce_sum, n_train, correct, bce_sum, n_valid, sum_label, mse_sum, q}
+ * row_mask (may be NULL = train_mask): the rows that contribute to the CE / accuracy sums; a
+ * multi-GPU caller whose rows are sharded passes train_mask AND owned-rows here while the edge
+ * terms keep testing both endpoints against the full train_mask.
  * ---------------------------------------------------------------------------------------- */
 int32_t sgs_loss_fwd(const float* logits, int64_t N, int64_t C, const int64_t* y,
-                     const uint8_t* train_mask, const int32_t* s_src, const int32_t* s_dst,
+                     const uint8_t* train_mask, const uint8_t* row_mask, const int32_t* s_src, const int32_t* s_dst,
                      const float* p_s, int64_t q, int32_t with_edges, double* acc, sgs_stream_t stream);
 /* loss_out[0] = c0*ce + c1*bce*[sum_label>1] + c2*mse (device float) from acc; a term whose
  * coefficient / flag is 0 is skipped entirely (c0 = 0 gives the stand-alone consistency loss). */
@@ -232,7 +247,7 @@ int32_t sgs_loss_finish(const double* acc, float c0, float c1, float c2, int32_t
 /* grads scaled by *gscale (device float, upstream dL/dloss): dlogits[N,C] (written: caller
  * zeroes), dp_s[q] (written). */
 int32_t sgs_loss_bwd(const float* logits, int64_t N, int64_t C, const int64_t* y,
-                     const uint8_t* train_mask, const int32_t* s_src, const int32_t* s_dst,
+                     const uint8_t* train_mask, const uint8_t* row_mask, const int32_t* s_src, const int32_t* s_dst,
                      const float* p_s, int64_t q, int32_t with_edges, const double* acc, float c0,
                      float c1, float c2, int32_t reg1, int32_t reg2, const float* gscale,
                      float* dlogits, float* dp_s, sgs_stream_t stream);

@@ -35,6 +35,8 @@ SIGNATURES = {
     "sgs_act_bwd": (I32, [P, P, I64, F32, P, P]),
     "sgs_colsum": (I32, [P, I64, I64, P, P]),
     "sgs_gcn_edge_grad": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, P]),
+    "sgs_gcn_edge_grad_partial": (I32, [P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P]),
+    "sgs_gcn_edge_grad_final": (I32, [P, P, P, P, P, P, I64, P, I32, P]),
     "sgs_gemm": (I32, [P, I64, I64, P, I64, I64, P, I64, I64, I64, I64, I32, I32, P]),
     "sgs_edge_score_workspace_bytes": (SZ, [I64, I64, I64, I32, I32]),
     "sgs_edge_score_fwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, SZ, I32, P]),
@@ -51,9 +53,9 @@ SIGNATURES = {
     "sgs_sample_topq": (I32, [P, P, P, I64, I64, F32, F32, I32, P, P, P, P, P, P, SZ, P]),
     "sgs_gather_selected": (I32, [P, P, P, I64, F32, F32, I32, P, P, P, P]),
     "sgs_scatter_selected": (I32, [P, P, I64, P, P]),
-    "sgs_loss_fwd": (I32, [P, I64, I64, P, P, P, P, P, I64, I32, P, P]),
+    "sgs_loss_fwd": (I32, [P, I64, I64, P, P, P, P, P, P, I64, I32, P, P]),
     "sgs_loss_finish": (I32, [P, F32, F32, F32, I32, I32, P, P]),
-    "sgs_loss_bwd": (I32, [P, I64, I64, P, P, P, P, P, I64, I32, P, F32, F32, F32, I32, I32, P, P, P, P]),
+    "sgs_loss_bwd": (I32, [P, I64, I64, P, P, P, P, P, P, I64, I32, P, F32, F32, F32, I32, I32, P, P, P, P]),
 }
 
 PREC_FP32, PREC_BF16, PREC_FP16, PREC_TF32 = 0, 1, 2, 3

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import dist as sdist
-from . import ops, sampling
+from . import ops, sampling, sharded
 from .ops import SAMPLE_TRAIN
 
 _softmax_cache = {}
@@ -170,7 +170,29 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
         optimizer_edge_prob.zero_grad()
         optimizer_gnn.zero_grad()
 
-        if mode == "learned":
+        if mode == "learned" and isinstance(batch, sharded.ShardedBatch):
+            # one graph sharded by destination range over the ranks; q is the global budget
+            if batch.num_edges_global <= q:
+                raise RuntimeError("sharded mode expects more edges than the budget q")
+            batch = batch.to(device)
+            r_ = (args.t_init - args.t_min) / max_epoch
+            temperature = max(args.t_min, args.t_init - epoch * r_)
+            loss, update_edge_mlp = sharded.learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q,
+                                                         _backward)
+            opts = (optimizer_edge_prob, optimizer_gnn) if update_edge_mlp else (optimizer_gnn,)
+            seen, plist = set(), []
+            for o in opts:
+                for grp in o.param_groups:
+                    for prm in grp["params"]:
+                        if id(prm) not in seen:
+                            seen.add(id(prm))
+                            plist.append(prm)
+            sharded.allreduce_partial_grads(plist, batch.comm)
+            if update_edge_mlp:
+                conditional_update += 1
+                optimizer_edge_prob.step()
+            optimizer_gnn.step()
+        elif mode == "learned":
             if batch.edge_index.shape[1] > q:
                 batch = batch.to(device)
                 # temperature anneal: computed and returned, never used by the sampler

@@ -393,6 +393,47 @@ int32_t sgs_colsum(const float* G, int64_t N, int64_t D, float* colsum, sgs_stre
   return SGS_OK;
 }
 
+// phases of sgs_gcn_edge_grad: 1 = SDDMM + per-node sums (tmp_g, tmp_t, tmp_a), 2 = final formula (dw).
+// A multi-GPU caller whose edges are sharded by destination all-reduces tmp_a[N] between the two.
+static int32_t edge_grad_impl(int phases, const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
+                              const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
+                              const int32_t* perm_src, const int32_t* src, const int32_t* dst, const float* G,
+                              const float* h, const float* dis, const float* deg, const float* loopw, int64_t M,
+                              int64_t N, int64_t D, float* tmp_g, float* tmp_t, float* tmp_a, float* dw,
+                              int32_t accumulate, cudaStream_t st) {
+  if (phases & 1) {
+    const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)G) % 16 == 0);
+#define SGS_SDDMM_LAUNCH(VEC, K)                                                                         \
+  edge_grad_sddmm_kernel<VEC, K><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, \
+                                                                 G, h, dis, loopw, N, (int)D, tmp_g, tmp_t, \
+                                                                 tmp_a, order_dst)
+    if (vec4 && D <= 128) SGS_SDDMM_LAUNCH(4, 1);
+    else if (vec4 && D <= 256) SGS_SDDMM_LAUNCH(4, 2);
+    else if (vec4 && D <= 512) SGS_SDDMM_LAUNCH(4, 4);
+    else if (vec4 && D <= 1024) SGS_SDDMM_LAUNCH(4, 8);
+    else if (D <= 32) SGS_SDDMM_LAUNCH(1, 1);
+    else if (D <= 64) SGS_SDDMM_LAUNCH(1, 2);
+    else if (D <= 128) SGS_SDDMM_LAUNCH(1, 4);
+    else if (D <= 256) SGS_SDDMM_LAUNCH(1, 8);
+    else {
+      set_error("sgs_gcn_edge_grad: unsupported width %lld", (long long)D);
+      return SGS_E_UNSUPPORTED;
+    }
+#undef SGS_SDDMM_LAUNCH
+    SGS_LAUNCH_CHECK();
+    edge_grad_srcsum_kernel<<<row_grid(N), kBlock, 0, st>>>(rowptr_src, perm_src, tmp_t, N, tmp_a);
+    SGS_LAUNCH_CHECK();
+  }
+  if (phases & 2) {
+    int64_t g = ceil_div(M, 256);
+    int64_t cap = (int64_t)sm_count() * 16;
+    edge_grad_final_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(src, dst, tmp_g, tmp_a, dis, deg, M, dw,
+                                                                          accumulate);
+    SGS_LAUNCH_CHECK();
+  }
+  return SGS_OK;
+}
+
 int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
                           const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
                           const int32_t* perm_src,
@@ -405,33 +446,30 @@ int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, co
   SGS_CHECK_ARG(rowptr_dst && perm_dst && nbr_dst && what_dst && rowptr_src && perm_src && src && dst && G &&
                     h && dis && deg && loopw && tmp_g && tmp_t && tmp_a && dw,
                 "null pointer");
-  cudaStream_t st = as_stream(stream);
-  const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)G) % 16 == 0);
-#define SGS_SDDMM_LAUNCH(VEC, K)                                                                         \
-  edge_grad_sddmm_kernel<VEC, K><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, \
-                                                                 G, h, dis, loopw, N, (int)D, tmp_g, tmp_t, \
-                                                                 tmp_a, order_dst)
-  if (vec4 && D <= 128) SGS_SDDMM_LAUNCH(4, 1);
-  else if (vec4 && D <= 256) SGS_SDDMM_LAUNCH(4, 2);
-  else if (vec4 && D <= 512) SGS_SDDMM_LAUNCH(4, 4);
-  else if (vec4 && D <= 1024) SGS_SDDMM_LAUNCH(4, 8);
-  else if (D <= 32) SGS_SDDMM_LAUNCH(1, 1);
-  else if (D <= 64) SGS_SDDMM_LAUNCH(1, 2);
-  else if (D <= 128) SGS_SDDMM_LAUNCH(1, 4);
-  else if (D <= 256) SGS_SDDMM_LAUNCH(1, 8);
-  else {
-    set_error("sgs_gcn_edge_grad: unsupported width %lld", (long long)D);
-    return SGS_E_UNSUPPORTED;
-  }
-#undef SGS_SDDMM_LAUNCH
-  SGS_LAUNCH_CHECK();
-  edge_grad_srcsum_kernel<<<row_grid(N), kBlock, 0, st>>>(rowptr_src, perm_src, tmp_t, N, tmp_a);
-  SGS_LAUNCH_CHECK();
-  int64_t g = ceil_div(M, 256);
-  int64_t cap = (int64_t)sm_count() * 16;
-  edge_grad_final_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(src, dst, tmp_g, tmp_a, dis, deg, M, dw,
-                                                                        accumulate);
-  SGS_LAUNCH_CHECK();
-  return SGS_OK;
+  return edge_grad_impl(3, rowptr_dst, perm_dst, nbr_dst, what_dst, order_dst, rowptr_src, perm_src, src, dst, G, h,
+                        dis, deg, loopw, M, N, D, tmp_g, tmp_t, tmp_a, dw, accumulate, as_stream(stream));
+}
+
+int32_t sgs_gcn_edge_grad_partial(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
+                                  const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
+                                  const int32_t* perm_src, const float* G, const float* h, const float* dis,
+                                  const float* loopw, int64_t M, int64_t N, int64_t D, float* tmp_g, float* tmp_t,
+                                  float* tmp_a, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && M > 0 && D > 0, "bad sizes");
+  SGS_CHECK_ARG(rowptr_dst && perm_dst && nbr_dst && what_dst && rowptr_src && perm_src && G && h && dis && loopw &&
+                    tmp_g && tmp_t && tmp_a,
+                "null pointer");
+  return edge_grad_impl(1, rowptr_dst, perm_dst, nbr_dst, what_dst, order_dst, rowptr_src, perm_src, nullptr, nullptr,
+                        G, h, dis, nullptr, loopw, M, N, D, tmp_g, tmp_t, tmp_a, nullptr, 0, as_stream(stream));
+}
+
+int32_t sgs_gcn_edge_grad_final(const int32_t* src, const int32_t* dst, const float* tmp_g, const float* tmp_a,
+                                const float* dis, const float* deg, int64_t M, float* dw, int32_t accumulate,
+                                sgs_stream_t stream) {
+  SGS_CHECK_ARG(M > 0, "bad sizes");
+  SGS_CHECK_ARG(src && dst && tmp_g && tmp_a && dis && deg && dw, "null pointer");
+  return edge_grad_impl(2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, src, dst, nullptr, nullptr,
+                        dis, deg, nullptr, M, 0, 0, const_cast<float*>(tmp_g), nullptr, const_cast<float*>(tmp_a), dw,
+                        accumulate, as_stream(stream));
 }
 }

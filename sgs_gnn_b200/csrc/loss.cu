@@ -213,14 +213,14 @@ using namespace sgs;
 extern "C" {
 
 int32_t sgs_loss_fwd(const float* logits, int64_t N, int64_t C, const int64_t* y, const uint8_t* train_mask,
-                     const int32_t* s_src, const int32_t* s_dst, const float* p_s, int64_t q, int32_t with_edges,
+                     const uint8_t* row_mask, const int32_t* s_src, const int32_t* s_dst, const float* p_s, int64_t q, int32_t with_edges,
                      double* acc, sgs_stream_t stream) {
   SGS_CHECK_ARG(N > 0 && C > 0 && q >= 0, "bad sizes");
   SGS_CHECK_ARG(logits && y && train_mask && acc, "null pointer");
   cudaStream_t st = as_stream(stream);
   SGS_CUDA(cudaMemsetAsync(acc, 0, 8 * sizeof(double), st));
-  loss_nodes_fwd_kernel<<<lgrid(kThreads / 32, N), kThreads, 0, st>>>(logits, N, (int)C, y, train_mask, acc,
-                                                                     (double)q);
+  loss_nodes_fwd_kernel<<<lgrid(kThreads / 32, N), kThreads, 0, st>>>(logits, N, (int)C, y,
+                                                                     row_mask ? row_mask : train_mask, acc, (double)q);
   SGS_LAUNCH_CHECK();
   if (with_edges && q > 0) {
     SGS_CHECK_ARG(s_src && s_dst && p_s, "null pointer (edges)");
@@ -240,14 +240,15 @@ int32_t sgs_loss_finish(const double* acc, float c0, float c1, float c2, int32_t
 }
 
 int32_t sgs_loss_bwd(const float* logits, int64_t N, int64_t C, const int64_t* y, const uint8_t* train_mask,
-                     const int32_t* s_src, const int32_t* s_dst, const float* p_s, int64_t q, int32_t with_edges,
+                     const uint8_t* row_mask, const int32_t* s_src, const int32_t* s_dst, const float* p_s, int64_t q, int32_t with_edges,
                      const double* acc, float c0, float c1, float c2, int32_t reg1, int32_t reg2,
                      const float* gscale, float* dlogits, float* dp_s, sgs_stream_t stream) {
   SGS_CHECK_ARG(N > 0 && C > 0 && q >= 0, "bad sizes");
   SGS_CHECK_ARG(logits && y && train_mask && acc && gscale && dlogits, "null pointer");
   cudaStream_t st = as_stream(stream);
-  loss_nodes_bwd_kernel<<<lgrid(kThreads / 32, N), kThreads, 0, st>>>(logits, N, (int)C, y, train_mask, acc, c0,
-                                                                     gscale, dlogits);
+  loss_nodes_bwd_kernel<<<lgrid(kThreads / 32, N), kThreads, 0, st>>>(logits, N, (int)C, y,
+                                                                     row_mask ? row_mask : train_mask, acc, c0, gscale,
+                                                                     dlogits);
   SGS_LAUNCH_CHECK();
   if (with_edges && q > 0) {
     SGS_CHECK_ARG(s_src && s_dst && p_s && dp_s, "null pointer (edges)");

@@ -88,28 +88,44 @@ class CudaTopQOps:
         self._lib.check(self._lib.lib().sgs_topq_hist(ops._p(keys), keys.numel(), ops._p(hist), ops._p(state), level,
                                                       ops._stream()), "sgs_topq_hist")
 
-    def compact(self, keys, state, tie_skip, q_cap):
+    def compact(self, keys, state, tie_skip, q_cap, n_expected=None):
         ops, lib = self._ops, self._lib.lib()
         e = keys.numel()
-        sel = torch.empty(max(q_cap, 1), dtype=torch.int32, device=keys.device)
+        cap = int(q_cap if n_expected is None else n_expected)
+        sel = torch.empty(max(cap, 1), dtype=torch.int32, device=keys.device)
         n_sel = torch.zeros(1, dtype=torch.int64, device=keys.device)
         ws = ops._ws(lib.sgs_topq_workspace_bytes(e), keys.device)
-        self._lib.check(lib.sgs_topq_compact(ops._p(keys), e, ops._p(state), int(tie_skip), ops._p(sel), int(q_cap),
+        self._lib.check(lib.sgs_topq_compact(ops._p(keys), e, ops._p(state), int(tie_skip), ops._p(sel), cap,
                                              None, ops._p(n_sel), ops._p(ws), ws.numel(), ops._stream()),
                         "sgs_topq_compact")
-        return sel[: int(n_sel.item())]
+        # n_expected comes from the local digit histograms: no host sync needed to size the output
+        return sel[:cap] if n_expected is not None else sel[: int(n_sel.item())]
+
+
+class TopQResult:
+    """sel: local ids (int32, ascending) of this rank's selected edges; state: the select's state
+    vector (tau bits at [2]); S: the global normaliser; invalid: any rank saw nan/inf/negative input;
+    n_global: number of edges selected over all ranks."""
+    __slots__ = ("sel", "state", "S", "invalid", "n_global", "tau_bits")
 
 
 class DistributedTopQ:
     """Global top-q over keys that live on different ranks; only histograms / counts move."""
 
+    SHIFT = (20, 9, 0)
+
     def __init__(self, local_ops=None, group=None):
         self.ops = local_ops if local_ops is not None else CudaTopQOps()
         self.group = group
 
-    def _allreduce(self, t):
+    def _allreduce(self, t, op=None):
         if is_dist():
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if t.is_cuda and dist.get_backend(self.group) == "gloo":
+                c = t.cpu()
+                dist.all_reduce(c, op=op or dist.ReduceOp.SUM, group=self.group)
+                t.copy_(c)
+            else:
+                dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
         return t
 
     def global_sum(self, p):
@@ -118,30 +134,72 @@ class DistributedTopQ:
         self._allreduce(s)
         return s.to(torch.float32)
 
-    def select(self, p, prob, noise, q_total, mode, coef=0.3, S=None):
-        """Returns (sel: local ids of this rank's selected edges in ascending order, state)."""
+    def _tie_cutoff(self, tied_gid, take):
+        """Smallest global edge id v such that `take` tied edges over all ranks have id <= v
+        (binary search on v; each probe all-reduces one count)."""
+        lo_v, hi_v = 0, (1 << 62)
+        top = tied_gid.max().reshape(1) if tied_gid.numel() else torch.zeros(1, dtype=torch.int64,
+                                                                             device=tied_gid.device)
+        self._allreduce(top, dist.ReduceOp.MAX)
+        hi_v = int(top.item())
+        while lo_v < hi_v:
+            mid = (lo_v + hi_v) // 2
+            cnt = (tied_gid <= mid).sum().reshape(1)
+            self._allreduce(cnt)
+            if int(cnt.item()) >= take:
+                hi_v = mid
+            else:
+                lo_v = mid + 1
+        return lo_v
+
+    def select_ex(self, p, prob, noise, q_total, mode, coef=0.3, S=None, gid=None):
+        """gid: global edge ids of the local edges (ascending).  Threshold ties are broken by lowest
+        GLOBAL edge id exactly as on one GPU; without gid, shards are assumed to be contiguous id
+        ranges in rank order."""
         if S is None and mode != 2:
             S = self.global_sum(p)
         keys, hist, state = self.ops.keys(p, prob, noise, mode, coef, S)
-        local_last = None
+        local = []
         for level in range(3):
             if level > 0:
                 self.ops.hist(keys, hist, state, level)
-            if level == 2:
-                local_last = hist.clone()
+            local.append(hist.clone())
             self._allreduce(hist)
             self.ops.find(hist, state, q_total, level)
-        # threshold ties: ranks take them in rank order (shards are ordered by edge id)
-        tau_bin = int(state[2].item()) & 511
-        n_eq_local = local_last[tau_bin].reshape(1).clone()
-        tie_skip = 0
-        if is_dist():
+        # one host read: tau, #ties to take, #ties overall, local ties, local #keys > tau, invalid flag
+        dev = state.device
+        tau_d = state[2] & 0x7FFFFFFF
+        ar = torch.arange(local[0].numel(), device=dev)
+        n_gt = sum((local[lv] * (ar > ((tau_d >> self.SHIFT[lv]) & (2047 if lv < 2 else 511)))).sum()
+                   for lv in range(3))
+        c_loc = local[2][(tau_d & 511)]
+        bad = state[5:6].clone()
+        self._allreduce(bad, dist.ReduceOp.MAX) if is_dist() else None
+        host = torch.stack([state[2], state[4], state[6], c_loc, n_gt, bad[0], state[3]]).cpu()
+        tau_bits, take, n_eq, c_r, n_gt_loc = (int(host[i]) for i in range(5))
+        if n_eq == take or not is_dist():
+            t_r = min(c_r, take)
+        elif gid is None:
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-            counts = [torch.zeros_like(n_eq_local) for _ in range(world)]
-            dist.all_gather(counts, n_eq_local, group=self.group)
-            tie_skip = int(sum(int(c.item()) for c in counts[:rank]))
-        sel = self.ops.compact(keys, state, tie_skip, p.numel())
-        return sel, state
+            counts = torch.zeros(world, dtype=torch.int64)
+            counts[rank] = c_r
+            self._allreduce(counts)
+            before = int(counts[:rank].sum())
+            t_r = max(0, min(c_r, take - before))
+        else:
+            tied = gid[torch.nonzero(keys == (tau_bits & 0x7FFFFFFF)).flatten()]
+            cut = self._tie_cutoff(tied, take)
+            t_r = int((tied <= cut).sum())
+        sel = self.ops.compact(keys, state, take - t_r, p.numel(), n_expected=n_gt_loc + t_r)
+        r = TopQResult()
+        r.sel, r.state, r.S, r.invalid = sel, state, S, bool(host[5])
+        r.n_global, r.tau_bits = int(host[6]) + take, tau_bits
+        return r
+
+    def select(self, p, prob, noise, q_total, mode, coef=0.3, S=None, gid=None):
+        """Returns (sel: local ids of this rank's selected edges in ascending order, state)."""
+        r = self.select_ex(p, prob, noise, q_total, mode, coef, S, gid)
+        return r.sel, r.state
 
 
 # ------------------------------------------------------------------------------------------

@@ -316,6 +316,17 @@ def linear_nt(x, w, precision=None, static_x=False):
     return gemm(x, k, 1, w, k, 1, m, n, k, precision=prec)
 
 
+def linear_nt_into(x, w, out, precision=None):
+    """out[M,N] = x[M,K] @ w[N,K]^T into a caller-provided (row-contiguous) buffer, e.g. a row slab."""
+    prec = _state["gemm"] if precision is None else precision
+    m, k, n = x.size(0), x.size(1), w.size(0)
+    if prec != PREC_FP32:
+        xa, lda = _rows_aligned16(x)
+        wa, ldb = _rows_aligned16(w)
+        return gemm(xa, lda, 1, wa, ldb, 1, m, n, k, out=out, precision=PREC_TF32)
+    return gemm(x, k, 1, w, k, 1, m, n, k, out=out, precision=prec)
+
+
 def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False):
     rowptr, _perm, nbr, order = csr
     n, d = h.shape
@@ -620,13 +631,14 @@ class LossStats:
     __slots__ = ("acc",)
 
 
-def loss_forward(logits, y, train_mask_u8, sub=None, p_s=None):
+def loss_forward(logits, y, train_mask_u8, sub=None, p_s=None, row_mask_u8=None):
     logits = _req(logits, torch.float32, "logits")
     n, c = logits.shape
     acc = torch.empty(8, dtype=torch.float64, device=logits.device)
     with_edges = sub is not None
     q = sub.num_edges if with_edges else 0
-    check(lib().sgs_loss_fwd(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(sub.src) if with_edges else None,
+    check(lib().sgs_loss_fwd(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(row_mask_u8),
+                             _p(sub.src) if with_edges else None,
                              _p(sub.dst) if with_edges else None, _p(p_s) if with_edges else None, q,
                              1 if with_edges else 0, _p(acc), _stream()), "sgs_loss_fwd")
     return acc
@@ -637,23 +649,24 @@ class FusedLossFn(torch.autograd.Function):
     (training_hybrid.py:103-132).  `acc` may be a precomputed sgs_loss_fwd accumulator."""
 
     @staticmethod
-    def forward(ctx, logits, p_s, y, train_mask_u8, sub, c0, c1, c2, reg1, reg2, acc):
+    def forward(ctx, logits, p_s, y, train_mask_u8, sub, c0, c1, c2, reg1, reg2, acc, row_mask_u8=None):
         logits = _req(logits, torch.float32, "logits")
         with_edges = sub is not None and p_s is not None and (reg1 or reg2)
         if with_edges:
             p_s = _req(p_s, torch.float32, "edge_probs")
         if acc is None:
-            acc = loss_forward(logits, y, train_mask_u8, sub if with_edges else None, p_s if with_edges else None)
+            acc = loss_forward(logits, y, train_mask_u8, sub if with_edges else None, p_s if with_edges else None,
+                               row_mask_u8)
         loss = torch.empty(1, dtype=torch.float32, device=logits.device)
         check(lib().sgs_loss_finish(_p(acc), c0, c1, c2, 1 if (reg1 and with_edges) else 0,
                                     1 if (reg2 and with_edges) else 0, _p(loss), _stream()), "sgs_loss_finish")
         ctx.sub, ctx.c0, ctx.c1, ctx.c2, ctx.reg1, ctx.reg2, ctx.with_edges = sub, c0, c1, c2, reg1, reg2, with_edges
-        ctx.save_for_backward(logits, p_s if with_edges else None, y, train_mask_u8, acc)
+        ctx.save_for_backward(logits, p_s if with_edges else None, y, train_mask_u8, acc, row_mask_u8)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        logits, p_s, y, tm, acc = ctx.saved_tensors
+        logits, p_s, y, tm, acc, rm = ctx.saved_tensors
         n, c = logits.shape
         sub = ctx.sub
         g = g.reshape(1).to(torch.float32).contiguous()
@@ -661,14 +674,14 @@ class FusedLossFn(torch.autograd.Function):
         dp = torch.empty_like(p_s) if ctx.with_edges else None
         q = sub.num_edges if ctx.with_edges else 0
         with _timed("loss_bwd"):
-          check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(sub.src) if ctx.with_edges else None,
+          check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(rm), _p(sub.src) if ctx.with_edges else None,
                                  _p(sub.dst) if ctx.with_edges else None, _p(p_s), q, 1 if ctx.with_edges else 0,
                                  _p(acc), ctx.c0, ctx.c1, ctx.c2, 1 if ctx.reg1 else 0, 1 if ctx.reg2 else 0, _p(g),
                                  _p(dlogits), _p(dp), _stream()), "sgs_loss_bwd")
-        return dlogits, dp, None, None, None, None, None, None, None, None, None
+        return dlogits, dp, None, None, None, None, None, None, None, None, None, None
 
 
 def fused_loss(logits, y, train_mask_u8, p_s=None, sub=None, c1=1.0, c2=0.5, reg1=True, reg2=True, acc=None,
-               c0=1.0):
+               c0=1.0, row_mask_u8=None):
     return FusedLossFn.apply(logits, p_s, y, train_mask_u8, sub, float(c0), float(c1), float(c2), bool(reg1),
-                             bool(reg2), acc)
+                             bool(reg2), acc, row_mask_u8)

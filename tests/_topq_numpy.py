@@ -44,10 +44,12 @@ class NumpyTopQOps:
             state[2], state[3], state[4], state[6] = prefix, k_total - (k - cum), k - cum, int(h[b])
         hist.zero_()
 
-    def compact(self, keys, state, tie_skip, q_cap):
+    def compact(self, keys, state, tie_skip, q_cap, n_expected=None):
         k = keys.numpy().astype(np.uint32)
         tau = np.uint32(int(state[2]))
         avail = max(int(state[4]) - tie_skip, 0)
         gt = np.nonzero(k > tau)[0]
         eq = np.nonzero(k == tau)[0][:avail]
-        return torch.from_numpy(np.sort(np.concatenate([gt, eq])).astype(np.int32))
+        sel = np.sort(np.concatenate([gt, eq])).astype(np.int32)
+        assert n_expected is None or n_expected == sel.size, (n_expected, sel.size)
+        return torch.from_numpy(sel)

@@ -53,7 +53,7 @@ def test_destination_ranges_partition_all_edges():
         assert max(sizes) - min(sizes) <= e // world * 0.25 + 200      # balanced by in-degree
 
 
-def _topq_worker(rank, world, e, q, ties):
+def _topq_worker(rank, world, e, q, ties, interleaved):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _topq_numpy import NumpyTopQOps
@@ -66,22 +66,35 @@ def _topq_worker(rank, world, e, q, ties):
     else:
         noise = ox.exponential_noise(e, g)
     prob = torch.softmax(torch.rand(e, generator=g), 0)
-    # contiguous id shards (rank order == edge id order)
-    lo, hi = rank * e // world, (rank + 1) * e // world
-    sel, state = sdist.DistributedTopQ(NumpyTopQOps()).select(p[lo:hi], prob[lo:hi], noise[lo:hi], q, 0, 0.3)
+    if interleaved:
+        # destination-range shards of a (src,dst)-sorted edge list interleave in edge-id order:
+        # ties at the threshold must still go to the lowest GLOBAL ids
+        owner = torch.randint(0, world, (e,), generator=g)
+        gid = torch.nonzero(owner == rank).flatten()
+    else:
+        # contiguous id shards (rank order == edge id order)
+        gid = torch.arange(rank * e // world, (rank + 1) * e // world)
+    r = sdist.DistributedTopQ(NumpyTopQOps()).select_ex(p[gid], prob[gid], noise[gid], q, 0, 0.3,
+                                                        gid=gid if interleaved else None)
+    assert r.n_global == q and not r.invalid
     gathered = [None] * world
-    dist.all_gather_object(gathered, (sel + lo).tolist())
+    dist.all_gather_object(gathered, gid[r.sel.long()].tolist())
     if rank == 0:
         got = sorted(i for part in gathered for i in part)
         S = p.sum(dtype=torch.float64).to(torch.float32)
         want = ox.sample_topq(p, prob, q, noise, 0.3, False, S=S)
         assert got == want.sel.tolist()
-        assert np.array([int(state[2])], dtype=np.uint32).view(np.float32)[0] == np.float32(want.tau)
+        assert np.array([r.tau_bits], dtype=np.uint32).view(np.float32)[0] == np.float32(want.tau)
 
 
 @pytest.mark.parametrize("ties", [False, True])
-def test_distributed_radix_select_matches_global_topq(ties):
-    _run(_topq_worker, 2, 5000, 1200, ties)
+@pytest.mark.parametrize("interleaved", [False, True])
+def test_distributed_radix_select_matches_global_topq(ties, interleaved):
+    _run(_topq_worker, 2, 5000, 1200, ties, interleaved)
+
+
+def test_distributed_radix_select_three_ranks_interleaved_ties():
+    _run(_topq_worker, 3, 3000, 700, True, True)
 
 
 def _dp_worker(rank, world):
