@@ -243,6 +243,11 @@ def run_gpu_arm(a):
         torch.cuda.cudart().cudaProfilerStart()
     launches0 = _lib.launch_count()
     learned = 0
+    tprof = None
+    if os.environ.get("SGS_TORCH_PROFILE"):   # debug aid: CUPTI kernel table of the timed steps (never a bench value)
+        from torch.profiler import ProfilerActivity, profile
+        tprof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+        tprof.__enter__()
     with ClockSampler(local) as clk, ops.KernelTimer() as kt:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -259,6 +264,10 @@ def run_gpu_arm(a):
             torch.cuda.cudart().cudaProfilerStop()
         ms = ev0.elapsed_time(ev1)
         ktot = kt.totals_ms()
+    if tprof is not None:
+        tprof.__exit__(None, None, None)
+        with open(os.environ["SGS_TORCH_PROFILE"] + f".rank{rank}.txt", "w") as fh:
+            fh.write(tprof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     launches = _lib.launch_count() - launches0
     clocks = clk.summary()
     if world > 1:

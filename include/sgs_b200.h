@@ -64,9 +64,11 @@ int32_t sgs_edge_index_gather(const int64_t* edge_index, int64_t M, const int32_
 
 size_t sgs_csr_workspace_bytes(int64_t M, int64_t N);
 /* Stable counting sort of the M edges by key (dst for the forward CSR, src for the backward
- * one): rowptr[N+1], perm[M] = edge ids in key order, nbr[M] = other[perm]; optional order[N] =
- * row ids sorted by descending degree (the SpMM / SDDMM kernels deal rows to warps in this order
- * so that power-law hub rows start first and the tail stays balanced). */
+ * one): rowptr[N+1], perm[M] = edge ids in key order, nbr[M] = other[perm]; optional order[N+1]:
+ * order[0..N) = row ids sorted by descending degree, order[N] = number of rows with more than
+ * SGS_HEAVY_ROW_DEG edges.  The SpMM / SDDMM kernels give each of those hub rows to a whole
+ * thread block and deal the rest to warps heaviest-first, so a power-law tail stays balanced. */
+#define SGS_HEAVY_ROW_DEG 512
 int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64_t N,
                       int32_t* rowptr, int32_t* perm, int32_t* nbr, int32_t* order, void* ws,
                       size_t ws_bytes, sgs_stream_t stream);
@@ -97,7 +99,7 @@ int32_t sgs_gcn_norm_apply(const int32_t* rowptr, const int32_t* perm, const int
 #define SGS_SPMM_DROPOUT 2
 #define SGS_SPMM_ACCUM 4
 int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what,
-                 const int32_t* order /* may be NULL */, const float* dis, const float* loopw,
+                 const int32_t* order /* [N+1] from sgs_csr_build, may be NULL */, const float* dis, const float* loopw,
                  const float* h, int64_t N, int64_t D, const float* bias, float* out, int32_t flags,
                  float p_drop, uint64_t seed, sgs_stream_t stream);
 

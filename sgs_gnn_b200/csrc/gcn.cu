@@ -72,31 +72,25 @@ gcn_what_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
 // (nbr, what) pairs are fetched 32 at a time (coalesced) and broadcast with shuffles so the
 // feature-row loads of consecutive neighbours are independent and stay in flight together.
 // ---------------------------------------------------------------------------------------
+// Rows with more than kHeavyDeg edges (power-law hubs; listed first in `order`, their number at order[N])
+// are processed by a whole block -- the 8 warps take interleaved 32-edge groups and their partial rows
+// are summed through shared memory in a fixed order -- so that one hub cannot become the kernel's tail.
 template <int VEC, int K>
-__global__ void __launch_bounds__(kBlock)
-spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
-            const float* __restrict__ what, const float* __restrict__ dis,
-            const float* __restrict__ loopw, const float* __restrict__ h, int64_t N, int D,
-            const float* __restrict__ bias, float* __restrict__ out, int flags, float p_drop,
-            uint64_t seed, const int32_t* __restrict__ order) {
-  const int lane = threadIdx.x & 31;
-  const int col0 = blockIdx.y * (32 * VEC * K);
-  int64_t idx = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
-  const uint32_t thr = dropout_threshold(p_drop);
-  const float scale = (flags & SGS_SPMM_DROPOUT) ? 1.0f / (1.0f - p_drop) : 1.0f;
+struct SpmmRow {
+  float acc[K][VEC];
 
-  // `order` lists the rows heaviest-first; dealing them round-robin to the warps balances the power-law tail
-  for (; idx < N; idx += step) {
-    const int64_t row = order ? order[idx] : idx;
-    float acc[K][VEC];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
+  }
 
-    const int beg = rowptr[row], end = rowptr[row + 1];
-    for (int base = beg; base < end; base += 32) {
+  // accumulate the edges [beg, end) taking 32-edge groups base = beg + 32*first, stride 32*nstep
+  __device__ __forceinline__ void gather(const int32_t* __restrict__ nbr, const float* __restrict__ what,
+                                         const float* __restrict__ h, int D, int col0, int lane, int beg, int end,
+                                         int first, int nstep) {
+    for (int base = beg + 32 * first; base < end; base += 32 * nstep) {
       int my_n = 0;
       float my_w = 0.f;
       if (base + lane < end) {
@@ -126,7 +120,13 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
         }
       }
     }
-    // self loop, bias, activation
+  }
+
+  // self loop, bias, activation, store
+  __device__ __forceinline__ void finish(int64_t row, const float* __restrict__ dis, const float* __restrict__ loopw,
+                                         const float* __restrict__ h, int D, int col0, int lane,
+                                         const float* __restrict__ bias, float* __restrict__ out, int flags,
+                                         float scale, uint32_t thr, uint64_t seed) {
     float selfw = 0.f;
     if (dis) {
       const float d = dis[row];
@@ -164,6 +164,56 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
       }
     }
   }
+};
+
+template <int VEC, int K>
+__global__ void __launch_bounds__(kBlock)
+spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+            const float* __restrict__ what, const float* __restrict__ dis,
+            const float* __restrict__ loopw, const float* __restrict__ h, int64_t N, int D,
+            const float* __restrict__ bias, float* __restrict__ out, int flags, float p_drop,
+            uint64_t seed, const int32_t* __restrict__ order) {
+  __shared__ float red[kWarpsPerBlock - 1][32 * VEC * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = blockIdx.y * (32 * VEC * K);
+  const uint32_t thr = dropout_threshold(p_drop);
+  const float scale = (flags & SGS_SPMM_DROPOUT) ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const int n_heavy = order ? order[N] : 0;
+  SpmmRow<VEC, K> r;
+
+  // phase 1: hub rows, one block per row
+  for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
+    const int64_t row = order[hidx];
+    r.clear();
+    r.gather(nbr, what, h, D, col0, lane, rowptr[row], rowptr[row + 1], warp, kWarpsPerBlock);
+    if (warp > 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) red[warp - 1][(k * 32 + lane) * VEC + v] = r.acc[k][v];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 0; w < kWarpsPerBlock - 1; ++w)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) r.acc[k][v] += red[w][(k * 32 + lane) * VEC + v];
+      r.finish(row, dis, loopw, h, D, col0, lane, bias, out, flags, scale, thr, seed);
+    }
+    __syncthreads();
+  }
+
+  // phase 2: one warp per row; `order` lists the rows heaviest-first, dealing them round-robin to the warps
+  // balances what is left of the power-law tail
+  int64_t idx = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; idx < N; idx += step) {
+    const int64_t row = order ? order[idx] : idx;
+    r.clear();
+    r.gather(nbr, what, h, D, col0, lane, rowptr[row], rowptr[row + 1], 0, 1);
+    r.finish(row, dis, loopw, h, D, col0, lane, bias, out, flags, scale, thr, seed);
+  }
 }
 
 __global__ void act_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, int64_t n,
@@ -192,12 +242,12 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
                        const float* __restrict__ dis, const float* __restrict__ loopw, int64_t N, int D,
                        float* __restrict__ tmp_g, float* __restrict__ tmp_t, float* __restrict__ tmp_a,
                        const int32_t* __restrict__ order) {
-  const int lane = threadIdx.x & 31;
-  int64_t idx = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (; idx < N; idx += step) {
-    const int64_t row = order ? order[idx] : idx;
-    float g_row[K][VEC];
+  __shared__ float red[kWarpsPerBlock];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_heavy = order ? order[N] : 0;
+  float g_row[K][VEC];
+
+  auto load_row = [&](int64_t row) {
     const float* gr = G + row * D;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -205,27 +255,29 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 #pragma unroll
       for (int t = 0; t < VEC; ++t) g_row[k][t] = (c + t < D) ? gr[c + t] : 0.f;
     }
-    auto partial_dot = [&](const float* hp) {
-      float d = 0.f;
+  };
+  auto partial_dot = [&](const float* hp) {
+    float d = 0.f;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int c = (k * 32 + lane) * VEC;
-        if (c < D) {
-          if (VEC == 4) {
-            const float4 x = *reinterpret_cast<const float4*>(hp + c);
-            d = fmaf(g_row[k][0], x.x, d);
-            d = fmaf(g_row[k][1], x.y, d);
-            d = fmaf(g_row[k][2], x.z, d);
-            d = fmaf(g_row[k][3], x.w, d);
-          } else {
-            d = fmaf(g_row[k][0], hp[c], d);
-          }
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * 32 + lane) * VEC;
+      if (c < D) {
+        if (VEC == 4) {
+          const float4 x = *reinterpret_cast<const float4*>(hp + c);
+          d = fmaf(g_row[k][0], x.x, d);
+          d = fmaf(g_row[k][1], x.y, d);
+          d = fmaf(g_row[k][2], x.z, d);
+          d = fmaf(g_row[k][3], x.w, d);
+        } else {
+          d = fmaf(g_row[k][0], hp[c], d);
         }
       }
-      return d;
-    };
-    auto dot_with = [&](const float* hp) { return warp_sum(partial_dot(hp)); };
-    const int beg = rowptr[row], end = rowptr[row + 1];
+    }
+    return d;
+  };
+  auto dot_with = [&](const float* hp) { return warp_sum(partial_dot(hp)); };
+  // g_e, t_e of the edges [beg, end) of the current row; returns sum t_e (valid in every lane)
+  auto edges = [&](int beg, int end) {
     float tsum = 0.f;
     // four neighbours per iteration: their row loads and shuffle reductions are independent (ILP)
     int i = beg;
@@ -262,12 +314,41 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     }
     tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
     tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+    return __shfl_sync(0xffffffffu, tsum, 0);
+  };
+  auto finish = [&](int64_t row, float tsum) {
     const float gl = dot_with(h + row * D);
     if (lane == 0) {
       const float d = dis[row];
       const float tl = gl * d * d * loopw[row];
       tmp_a[row] = tsum + 2.0f * tl;
     }
+  };
+
+  // phase 1: hub rows (first n_heavy entries of `order`), the block's warps take contiguous edge ranges
+  for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
+    const int64_t row = order[hidx];
+    load_row(row);
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    const int per = (((end - beg) + kWarpsPerBlock - 1) / kWarpsPerBlock + 3) & ~3;
+    const int b = min(end, beg + warp * per), e = min(end, b + per);
+    const float part = edges(b, e);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+      float tsum = 0.f;
+      for (int w = 0; w < kWarpsPerBlock; ++w) tsum += red[w];
+      finish(row, tsum);
+    }
+    __syncthreads();
+  }
+  // phase 2: one warp per row
+  int64_t idx = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; idx < N; idx += step) {
+    const int64_t row = order ? order[idx] : idx;
+    load_row(row);
+    finish(row, edges(rowptr[row], rowptr[row + 1]));
   }
 }
 

@@ -88,6 +88,15 @@ __global__ void degree_keys_kernel(const int32_t* __restrict__ rowptr, int64_t N
   }
 }
 
+// order[N] = number of rows with more than SGS_HEAVY_ROW_DEG edges (they come first in `order`)
+__global__ void heavy_count_kernel(const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ count) {
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    c += (rowptr[i + 1] - rowptr[i]) > SGS_HEAVY_ROW_DEG;
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 }  // namespace sgs
 
 using namespace sgs;
@@ -143,6 +152,9 @@ static int32_t degree_order(const int32_t* rowptr, int64_t N, int32_t* order, vo
   SGS_CUDA(cub::DeviceRadixSort::SortPairs(temp, need, dk, dv, (int)N, 0, 32, st));
   count_launch(4);
   SGS_CUDA(cudaMemcpyAsync(order, dv.Current(), N * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  SGS_CUDA(cudaMemsetAsync(order + N, 0, sizeof(int32_t), st));
+  heavy_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N, 256), 1024), 256, 0, st>>>(rowptr, N, order + N);
+  SGS_LAUNCH_CHECK();
   return SGS_OK;
 }
 

@@ -113,6 +113,7 @@ class DistributedTopQ:
     """Global top-q over keys that live on different ranks; only histograms / counts move."""
 
     SHIFT = (20, 9, 0)
+    TIE_GATHER_MAX = 1 << 16
 
     def __init__(self, local_ops=None, group=None):
         self.ops = local_ops if local_ops is not None else CudaTopQOps()
@@ -127,6 +128,14 @@ class DistributedTopQ:
             else:
                 dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def _allgather(self, t, world):
+        staged = t.is_cuda and dist.get_backend(self.group) == "gloo"
+        src = t.cpu() if staged else t
+        out = torch.empty(world * src.numel(), dtype=src.dtype, device=src.device)
+        dist.all_gather_into_tensor(out, src.reshape(-1), group=self.group)
+        out = out.view((world,) + tuple(src.shape))
+        return out.to(t.device) if staged else out
 
     def global_sum(self, p):
         """S = sum over all ranks of p, accumulated in fp64 and rounded once (identical on every rank)."""
@@ -187,9 +196,19 @@ class DistributedTopQ:
             before = int(counts[:rank].sum())
             t_r = max(0, min(c_r, take - before))
         else:
+            # fp32 keys collide routinely at 10^8 edges: n_eq is a handful.  All-gather the tied global ids
+            # (padded to n_eq) and cut at the take-th smallest -- one collective, one more host read.
             tied = gid[torch.nonzero(keys == (tau_bits & 0x7FFFFFFF)).flatten()]
-            cut = self._tie_cutoff(tied, take)
-            t_r = int((tied <= cut).sum())
+            if n_eq <= self.TIE_GATHER_MAX:
+                world = dist.get_world_size(self.group)
+                mine = torch.full((n_eq,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=tied.device)
+                mine[: tied.numel()] = tied
+                every = self._allgather(mine, world)
+                cut = torch.sort(every.flatten()).values[take - 1]
+                t_r = int((tied <= cut).sum())
+            else:
+                cut = self._tie_cutoff(tied, take)
+                t_r = int((tied <= cut).sum())
         sel = self.ops.compact(keys, state, take - t_r, p.numel(), n_expected=n_gt_loc + t_r)
         r = TopQResult()
         r.sel, r.state, r.S, r.invalid = sel, state, S, bool(host[5])

@@ -205,7 +205,7 @@ class Graph:
         rowptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
         perm = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
         nbr = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
-        order = torch.empty(n, dtype=torch.int32, device=self.device)
+        order = torch.empty(n + 1, dtype=torch.int32, device=self.device)   # [N] = number of hub rows
         nbytes = lib().sgs_csr_workspace_bytes(m, n)
         ws = _ws(nbytes, self.device)
         with _timed("csr_build"):

@@ -53,11 +53,13 @@ def test_destination_ranges_partition_all_edges():
         assert max(sizes) - min(sizes) <= e // world * 0.25 + 200      # balanced by in-degree
 
 
-def _topq_worker(rank, world, e, q, ties, interleaved):
+def _topq_worker(rank, world, e, q, ties, interleaved, gather_max=None):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _topq_numpy import NumpyTopQOps
     from sgs_gnn_b200 import dist as sdist
+    if gather_max is not None:      # force the binary-search fallback of the tie resolution
+        sdist.DistributedTopQ.TIE_GATHER_MAX = gather_max
     g = torch.Generator().manual_seed(123)
     p = torch.rand(e, generator=g)
     if ties:
@@ -93,8 +95,9 @@ def test_distributed_radix_select_matches_global_topq(ties, interleaved):
     _run(_topq_worker, 2, 5000, 1200, ties, interleaved)
 
 
-def test_distributed_radix_select_three_ranks_interleaved_ties():
-    _run(_topq_worker, 3, 3000, 700, True, True)
+@pytest.mark.parametrize("gather_max", [None, 4])
+def test_distributed_radix_select_three_ranks_interleaved_ties(gather_max):
+    _run(_topq_worker, 3, 3000, 700, True, True, gather_max)
 
 
 def _dp_worker(rank, world):

@@ -74,6 +74,41 @@ def test_gcn_conv_forward_backward(dev, d, weighted):
             assert relerr(a.cpu(), r) < RTOL, name
 
 
+@pytest.mark.parametrize("d", [41, 256])
+def test_gcn_conv_hub_rows(dev, d):
+    """Power-law hubs: rows with more than SGS_HEAVY_ROW_DEG (512) in- or out-edges take the block-cooperative
+    path of the SpMM / SDDMM kernels; two hubs (one in, one out, 3000 and 1500 edges) among ordinary rows."""
+    from sgs_gnn_b200 import ops
+    n, f = 4000, 32
+    g = torch.Generator().manual_seed(17 + d)
+    base = _rand_graph(n, 8000, 3)
+    hub_in = torch.stack([torch.randperm(n - 1, generator=g)[:3000] + 1, torch.zeros(3000, dtype=torch.int64)])
+    hub_out = torch.stack([torch.full((1500,), 7, dtype=torch.int64), torch.randperm(n - 8, generator=g)[:1500] + 8])
+    ei = torch.cat([base, hub_in, hub_out], 1)
+    ei = ei[:, torch.randperm(ei.size(1), generator=g)]
+    m = ei.size(1)
+    x = torch.randn(n, f, generator=g)
+    W = torch.randn(d, f, generator=g) * 0.2
+    b = torch.randn(d, generator=g) * 0.1
+    w = torch.rand(m, generator=g)
+    G = torch.randn(n, d, generator=g)
+    xr, Wr, br, wr = (v.clone().requires_grad_(True) for v in (x, W, b, w))
+    out_ref = torch.relu(ox.gcn_conv(xr, Wr, br, ei, wr))
+    grads_ref = torch.autograd.grad((out_ref * G).sum(), [xr, Wr, br, wr])
+    xd, Wd, bd, wd = (v.to(dev).requires_grad_(True) for v in (x, W, b, w))
+    graph = ops.graph_of(ei.to(dev), n)
+    assert int(graph.csr_dst[3][n]) >= 1 and int(graph.csr_src[3][n]) >= 1      # hub rows were detected
+    out = ops.gcn_conv(xd, Wd, bd, graph, wd, relu=True)
+    assert relerr(out.detach().cpu(), out_ref.detach()) < RTOL
+    grads = torch.autograd.grad((out * G.to(dev)).sum(), [xd, Wd, bd, wd])
+    keep = ei[0] != ei[1]
+    for name, a, r in zip(("dx", "dW", "db", "dw"), grads, grads_ref):
+        if name == "dw":
+            assert relerr(a.cpu()[keep], r[keep]) < RTOL, name
+        else:
+            assert relerr(a.cpu(), r) < RTOL, name
+
+
 def test_gcn_norm_edge_cases(dev):
     from sgs_gnn_b200 import ops
     # isolated nodes, duplicate edges, an input self loop carrying a weight
