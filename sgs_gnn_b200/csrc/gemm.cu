@@ -5,6 +5,8 @@
 
 namespace sgs {
 
+int32_t gemm_tc_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                   int64_t N, int64_t K, int32_t accumulate, int32_t precision, cudaStream_t st);
 int32_t gemm_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, int32_t accumulate, int32_t precision, cudaStream_t st);
 
@@ -95,7 +97,10 @@ extern "C" int32_t sgs_gemm(const float* A, int64_t a_sm, int64_t a_sk, const fl
   cudaStream_t st = as_stream(stream);
   if (precision != SGS_PREC_FP32) {
     if (a_sk == 1 && b_sk == 1 && K > 0) return gemm_tc(A, a_sm, B, b_sn, C, ldc, M, N, K, accumulate, precision, st);
-    set_error("sgs_gemm: tensor-core modes need unit stride along K for both operands");
+    // TN form: both operands have unit stride along M / N (reduction over their rows)
+    if (a_sm == 1 && b_sn == 1 && K > 0)
+      return gemm_tc_tn(A, a_sk, B, b_sk, C, ldc, M, N, K, accumulate, precision, st);
+    set_error("sgs_gemm: tensor-core modes need unit stride along K (NT) or along M and N (TN) for both operands");
     return SGS_E_UNSUPPORTED;
   }
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);

@@ -38,9 +38,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Blocking wait.  The retry loop lives inside the asm block (two instructions per retry, no compiler-inserted
+// YIELD / R2UR / predicate shuffling) and try_wait carries a suspend-time hint, so a waiting warp sleeps in
+// hardware instead of burning the issue slots of the producer / epilogue warps that share its scheduler
+// (ncu r01: spin instructions were ~27% of all issued instructions of the scorer kernel).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "MBAR_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra MBAR_WAIT_DONE;\n\t"
+      "bra MBAR_WAIT_LOOP;\n\t"
+      "MBAR_WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / TMA reads)
@@ -154,6 +167,19 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// MN-major operand of 32-bit elements (kind::tf32): SWIZZLE_128B with 32-byte atoms (layout type 1; TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Rows are 128 B (32 elements along MN), the 32-byte chunk c of row r sits
+// at chunk c ^ (r & 3); 4-row groups along K are 512 B apart (SBO), 32-element blocks along MN `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 

@@ -327,6 +327,22 @@ def linear_nt_into(x, w, out, precision=None):
     return gemm(x, k, 1, w, k, 1, m, n, k, out=out, precision=prec)
 
 
+def gemm_tn(a, b, out=None, static_b=False, precision=None):
+    """out[M,N] = a[K,M]^T @ b[K,N] (weight gradients dW = dh^T x: a reduction over the K node rows).
+    Tensor-core mode: tcgen05 kind::tf32 with MN-major operands straight from the row-major tensors, K split
+    over the CTAs; needs 16-byte aligned row strides (odd widths fall back to the fp32 split-K kernel, a static
+    `b` such as the node features is padded once)."""
+    prec = _state["gemm"] if precision is None else precision
+    k, m = a.shape
+    n = b.size(1)
+    if prec != PREC_FP32 and m % 4 == 0 and a.data_ptr() % 16 == 0:
+        bb, ldb = (b, n) if (n % 4 == 0 and b.data_ptr() % 16 == 0) else (_rows_aligned16(b, cache=True) if static_b
+                                                                          else (None, 0))
+        if bb is not None:
+            return gemm(a, 1, m, bb, 1, ldb, m, n, k, out=out, precision=PREC_TF32)
+    return gemm(a, 1, m, b, 1, n, m, n, k, out=out, precision=PREC_FP32)
+
+
 def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False):
     rowptr, _perm, nbr, order = csr
     n, d = h.shape
@@ -380,9 +396,8 @@ class GCNConvFn(torch.autograd.Function):
         if need_w or need_x:
             dh = spmm(graph.csr_src, norm.what_src, norm, g)
             fin = x.size(1)
-            # reductions over the node dimension stay on the fp32 split-K path (MN-major operands)
             if need_w:  # dW[d, fin] = dh^T x
-                dw = gemm(dh, 1, d, x, 1, fin, d, fin, n, precision=PREC_FP32)
+                dw = gemm_tn(dh, x, static_b=not x.requires_grad)
             if need_x:  # dx[n, fin] = dh W
                 dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d, precision=PREC_FP32)
         if need_ew and ctx.has_w:

@@ -319,7 +319,13 @@ class ShardedGCNConvFn(torch.autograd.Function):
             if need_w:
                 dw = torch.zeros_like(weight)
                 if ns > 0:
-                    ops.gemm(dh_slab, 1, d, x[lo:hi], 1, fin, d, fin, ns, out=dw, precision=PREC_FP32)
+                    xs = x
+                    if fin % 4 and not x.requires_grad:      # static features: the padded copy is 16-byte aligned
+                        xs = ops._rows_aligned16(x, cache=True)[0]
+                    ops.gemm_tn(dh_slab, xs[lo:hi], out=dw) if xs is x else \
+                        ops.gemm(dh_slab, 1, d, xs[lo:hi], 1, xs.size(1), d, fin, ns, out=dw,
+                                 precision=ops._state["gemm"] if (d % 4 == 0 and ops._state["gemm"] != PREC_FP32)
+                                 else PREC_FP32)
             if need_x:
                 dx = torch.zeros(n, fin, dtype=torch.float32, device=gout.device)
                 if ns > 0:

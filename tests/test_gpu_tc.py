@@ -140,3 +140,24 @@ def test_gemm_tf32_tma(dev, m, n, k):
     assert got.shape == (m, n) and err < 2e-3, err
     ref32 = ops.linear_nt(a.to(dev), b.to(dev), precision=ops.PREC_FP32).cpu()
     assert float((ref32 - want).abs().max() / want.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("k,m,n", [(4096, 256, 602), (1000, 128, 128), (70000, 256, 256), (513, 64, 36), (33, 8, 4)])
+def test_gemm_tf32_tn_splitk(dev, k, m, n):
+    """K4 weight-gradient form dW = A^T B (A [K,M], B [K,N]): tcgen05 kind::tf32 with MN-major operands and the
+    K range split over CTAs.  Stated bound for tf32 operands: 2e-3 of max |C|."""
+    from sgs_gnn_b200 import ops
+    g = torch.Generator().manual_seed(k + m + n)
+    a = torch.randn(k, m, generator=g)
+    b = torch.randn(k, n, generator=g)
+    want = (a.double().t() @ b.double()).float()
+    got = ops.gemm_tn(a.to(dev), b.to(dev), static_b=True, precision=ops.PREC_TF32).cpu()
+    err = float((got - want).abs().max() / want.abs().max())
+    assert got.shape == (m, n) and err < 2e-3, err
+    ref32 = ops.gemm_tn(a.to(dev), b.to(dev), precision=ops.PREC_FP32).cpu()
+    assert float((ref32 - want).abs().max() / want.abs().max()) < 1e-5
+    # accumulate into an existing C
+    c0 = torch.ones(m, n, device=dev)
+    got2 = ops.gemm(a.to(dev), 1, m, ops._rows_aligned16(b.to(dev))[0], 1, (n + 3) // 4 * 4, m, n, k, out=c0,
+                    accumulate=True, precision=ops.PREC_TF32).cpu()
+    assert float((got2 - want - 1.0).abs().max() / want.abs().max()) < 2e-3
