@@ -52,19 +52,26 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
-// Dropout keep decisions: a 32-bit per-row key (one splitmix64 per (seed, row)), then one cheap 32-bit
-// mix per PAIR of columns whose two 16-bit halves are compared against the threshold.
+// Dropout keep decisions: a 32-bit per-row key (one splitmix64 per (seed, row)), then per PAIR of columns one
+// xor with a column constant and two multiplicative hashes whose top 16 bits are compared with the threshold.
+// The hot epilogues test `x * M >= threshold << 16` directly (one IMAD + one ISETP per column, no extraction).
+constexpr uint32_t kDropMulEven = 0x85EBCA6Bu, kDropMulOdd = 0xC2B2AE35u;
 __host__ __device__ __forceinline__ uint32_t dropout_rowkey(uint64_t seed, uint64_t row) {
   return (uint32_t)(splitmix64(seed + row * 0xD6E8FEB86659FD93ull) >> 32);
 }
+// column-pair constant: separable in (colpair >> 4, colpair & 15) so that a 32-column chunk of an unrolled loop
+// needs one runtime xor (chunk part) and otherwise only immediates
+__host__ __device__ __forceinline__ uint32_t dropout_colmix(uint32_t colpair) {
+  return ((colpair >> 4) * 0x9E3779B9u) ^ ((colpair & 15u) * 0x7FEB352Du);
+}
 // 32 random bits for columns (2*colpair, 2*colpair + 1): low half -> even column, high half -> odd column
 __host__ __device__ __forceinline__ uint32_t dropout_pair(uint32_t rowkey, uint32_t colpair) {
-  uint32_t h = rowkey ^ (colpair * 0x9E3779B9u);
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  return h;
+  const uint32_t x = rowkey ^ dropout_colmix(colpair);
+  return ((x * kDropMulEven) >> 16) | ((x * kDropMulOdd) & 0xFFFF0000u);
+}
+// threshold for the direct 32-bit compare: keep iff x * M >= dropout_threshold32(p)  (p < 1)
+__host__ __device__ __forceinline__ uint32_t dropout_threshold32(uint32_t thr16) {
+  return thr16 >= 65536u ? 0xFFFFFFFFu : (thr16 << 16);
 }
 // 64 bits = four 16-bit lanes for the 4 consecutive columns [4*col4, 4*col4 + 4)
 __host__ __device__ __forceinline__ uint64_t dropout_bits_rk(uint32_t rowkey, uint32_t col4) {

@@ -206,6 +206,7 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         for (int sp = 0; sp < NSP; ++sp, ++it) {
           const uint32_t slot = it % NSTAGE;
           mbar_wait(full0 + 8 * slot, (it / NSTAGE) & 1);
+          fence_proxy_async_smem();   // producers' generic-proxy stores -> async proxy (see scorer_producer.cuh)
           tc_fence_after();
 #pragma unroll
           for (int half = 0; half < 2; ++half)

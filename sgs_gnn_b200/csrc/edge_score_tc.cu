@@ -12,6 +12,8 @@
 // (tmem_full/tmem_empty), so gathers, MMAs and the epilogue of consecutive tiles overlap.
 // K is ordered in pairs of 64-column blocks [product cols 64j.. | difference cols 64j..] so one
 // gathered 16-byte chunk of x and y feeds both blocks of the same stage.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc.cuh"
 #include "scorer_producer.cuh"
@@ -175,6 +177,7 @@ edge_score_tc_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src,
         for (int sp = 0; sp < NSP; ++sp, ++it) {
           const uint32_t slot = it % NSTAGE;
           mbar_wait(full0 + 8 * slot, (it / NSTAGE) & 1);
+          fence_proxy_async_smem();   // producers' generic-proxy stores -> async proxy (see scorer_producer.cuh)
           tc_fence_after();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -275,6 +278,20 @@ size_t edge_score_tc_workspace_bytes(int64_t n, int64_t N, int64_t H) {
   return 1024 + (size_t)N * H * 2 + (nb > 1 ? (size_t)nb * n * 4 : 0);
 }
 
+int32_t edge_score_fwd_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
+                            const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
+                            const float* b2, float p_drop, uint64_t seed, float* p, cudaStream_t st);
+
+// SGS_K1_SINGLE_CTA=1 selects the single-CTA kernel for H = 256 (A/B measurements)
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGS_K1_SINGLE_CTA");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <typename T, int BN, int H>
 static int32_t launch_k1(const float* out, int64_t N, const int32_t* src, const int32_t* dst, const int32_t* ids,
                          int64_t n, const float* W1, const float* b1, const float* w2, const float* b2,
@@ -291,6 +308,10 @@ static int32_t launch_k1(const float* out, int64_t N, const int32_t* src, const 
   const int64_t cap = (int64_t)sm_count() * 16;
   convert_rows_kernel<T><<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(out, n8, reinterpret_cast<uint4*>(tab));
   SGS_LAUNCH_CHECK();
+  if (H == 256 && use_cta_pairs()) {
+    // CTA pairs (cta_group::2): every 128-edge tile is gathered and built once instead of once per W1 slice
+    return edge_score_fwd_pair(tab, Cvt<T>::kFmt == 1, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, st);
+  }
   const size_t smem = k1_smem_bytes(BN, H);
   auto kern = edge_score_tc_kernel<T, BN, H>;
   SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -7,12 +7,16 @@
 //   * the edge endpoints (src/dst ids) of tile t+1 are loaded while tile t is being built,
 //   * the row chunks of stage g+1 (possibly the first stage of the next tile) are in flight while stage g is
 //     converted and stored.
+// CONTRACT: the consumer must execute fence_proxy_async_smem() after waiting on the stage's full barrier and before
+// its tcgen05.mma reads the stage.
 #pragma once
 #include "tc.cuh"
 
 namespace sgs {
 
-template <typename T, int H, int NSTAGE, int STAGE_BYTES, int TILE_M>
+// PAIR: the CTA is one half of a cta_group::2 pair -- the "stage full" barrier lives in the leader CTA (full0 is then
+// a shared::cluster address and arrivals are released at cluster scope).
+template <typename T, int H, int NSTAGE, int STAGE_BYTES, int TILE_M, bool PAIR = false>
 struct FeatureProducer {
   static constexpr int NSP = H / 64;
 
@@ -84,8 +88,12 @@ struct FeatureProducer {
               make_uint4(Cvt<T>::sub2(cx[i].x, cy[i].x), Cvt<T>::sub2(cx[i].y, cy[i].y),
                          Cvt<T>::sub2(cx[i].z, cy[i].z), Cvt<T>::sub2(cx[i].w, cy[i].w));
         }
-        fence_proxy_async_smem();
-        mbar_arrive(full0 + 8 * slot);
+        // No proxy fence here: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR waits
+        // for this thread's in-flight prefetch loads, i.e. it would expose the full gather latency once per stage
+        // (ncu r01: ~22% of the stall samples).  The CTA-scope release of the arrive orders the stores before the
+        // consumer's acquire; the consumer (one thread, nothing in flight) issues the proxy fence before its MMAs.
+        if (PAIR) mbar_arrive_cluster(full0 + 8 * slot);
+        else mbar_arrive(full0 + 8 * slot);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           cx[i] = nx[i];

@@ -23,12 +23,11 @@ def dropout_threshold(p):
 
 def _pair_hash(rowkey, colpair):
     with np.errstate(over="ignore"):
-        h = rowkey ^ (colpair * np.uint32(0x9E3779B9))
-        h = h * np.uint32(0x85EBCA6B)
-        h = h ^ (h >> np.uint32(13))
-        h = h * np.uint32(0xC2B2AE35)
-        h = h ^ (h >> np.uint32(16))
-    return h
+        mix = ((colpair >> np.uint32(4)) * np.uint32(0x9E3779B9)) ^ ((colpair & np.uint32(15)) * np.uint32(0x7FEB352D))
+        x = rowkey ^ mix
+        lo = (x * np.uint32(0x85EBCA6B)) >> np.uint32(16)
+        hi = (x * np.uint32(0xC2B2AE35)) & np.uint32(0xFFFF0000)
+    return lo | hi
 
 
 def keep_mask(seed, rows, ncols, p):
