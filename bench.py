@@ -66,6 +66,8 @@ class ClockSampler:
         self.path = None
 
     def __enter__(self):
+        if os.environ.get("SGS_NO_CLOCKS"):
+            return self
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
@@ -222,6 +224,11 @@ def run_gpu_arm(a):
     model, og, oe, oa = build_model(f, c, dev, a.drop_rate)
     args = make_args(dev, a.drop_rate)
     args.data_parallel = world > 1 and not shard   # independent graph batches per rank + weight-gradient all-reduce
+    # The reference's conditional gate (training_hybrid.py:92-101) skips the scorer backward whenever the random
+    # baseline wins, which makes a step ~2x cheaper.  By default the bench computes the gate (both forwards, the
+    # accuracy counters, the host read) but then always takes the learned-wins branch, so every timed step does the
+    # full work and runs are comparable across seeds and GPU counts; --gate natural follows the reference.
+    args.force_branch = "learned" if a.gate == "learned" else None
     crit = nn.CrossEntropyLoss()
 
     def barrier():
@@ -262,7 +269,10 @@ def run_gpu_arm(a):
     profiling = bool(os.environ.get("SGS_CUDA_PROFILER"))
     if profiling:
         torch.cuda.cudart().cudaProfilerStart()
+    if os.environ.get("SGS_MEM_HISTORY"):
+        torch.cuda.memory._record_memory_history(max_entries=200000)
     launches0 = _lib.launch_count()
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     learned = 0
     tprof = None
     if os.environ.get("SGS_TORCH_PROFILE"):   # debug aid: CUPTI kernel table of the timed steps (never a bench value)
@@ -271,6 +281,11 @@ def run_gpu_arm(a):
         tprof.__enter__()
     with ClockSampler(local) as clk, ops.KernelTimer() as kt:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cprof = None
+        if os.environ.get("SGS_CPROFILE"):     # debug aid: host-side cost of a step
+            import cProfile
+            cprof = cProfile.Profile()
+            cprof.enable()
         ev0.record()
         for s in range(a.steps):
             t_s = time.perf_counter()
@@ -280,6 +295,13 @@ def run_gpu_arm(a):
                 print(f"[rank {rank}] step {s}: {1e3 * (time.perf_counter() - t_s):.1f} ms (learned={n_cond})",
                       file=sys.stderr, flush=True)
         ev1.record()
+        if cprof is not None:
+            cprof.disable()
+            import io
+            import pstats
+            buf = io.StringIO()
+            pstats.Stats(cprof, stream=buf).sort_stats("tottime").print_stats(45)
+            open(os.environ["SGS_CPROFILE"] + f".rank{rank}.txt", "w").write(buf.getvalue())
         barrier()
         if profiling:
             torch.cuda.cudart().cudaProfilerStop()
@@ -290,6 +312,21 @@ def run_gpu_arm(a):
         with open(os.environ["SGS_TORCH_PROFILE"] + f".rank{rank}.txt", "w") as fh:
             fh.write(tprof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     launches = _lib.launch_count() - launches0
+    if os.environ.get("SGS_MEM_HISTORY"):      # debug aid: who called cudaMalloc inside the timed region
+        snap = torch.cuda.memory._snapshot()
+        import collections
+        cnt = collections.Counter()
+        for tr in snap.get("device_traces", []):
+            for ev in tr:
+                if ev.get("action") in ("segment_alloc", "segment_free"):
+                    fr = [f for f in ev.get("frames", []) if "sgs_gnn_b200" in f.get("filename", "") or "bench.py" in f.get("filename", "")]
+                    where = " <- ".join(f"{os.path.basename(f['filename'])}:{f['line']}({f['name']})" for f in fr[:3])
+                    cnt[(ev["action"], ev.get("size", 0) >> 20, where)] += 1
+        with open(os.environ["SGS_MEM_HISTORY"] + f".rank{rank}.txt", "w") as fh:
+            for k, v in cnt.most_common(60):
+                fh.write(f"{v:4d}  {k[0]:14s} {k[1]:8d} MiB  {k[2]}\n")
+        torch.cuda.memory._record_memory_history(enabled=None)
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0   # cudaMalloc calls while timed
     clocks = clk.summary()
     if world > 1:
         tms = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -392,7 +429,10 @@ def run_gpu_arm(a):
                                    ("" if a.scale == 1.0 else f" (scaled {a.scale:g}x)"),
                        "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
                        "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": "hybrid",
-                       "conditional": True, "scorer_precision": a.precision, "gemm_precision": a.gemm_precision,
+                       "conditional": True,
+                       "gate": ("forced learned-wins: both forwards + gate are computed, then every step runs the full "
+                                "learned branch incl. the scorer backward" if a.gate == "learned" else "natural"),
+                       "scorer_precision": a.precision, "gemm_precision": a.gemm_precision,
                        "parallelism": "single" if world == 1 else (
                            f"shard{world}: one graph, edges sharded by destination-node range; distributed radix "
                            "top-q (digit-histogram all-reduce), slab all-gather / reduce-scatter, partial weight-grad "
@@ -401,7 +441,8 @@ def run_gpu_arm(a):
                        "l2_policy": "inputs larger than L2 (graph + features >> 126 MB)",
                        "learned_wins_steps": learned},
             "epochs_per_s": units * a.steps / (ms * 1e-3), "scored_edges_per_s": units * e * a.steps / (ms * 1e-3),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": int(mallocs),
+            "roofline": roofline,
             "kernel_time_share": shares, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -424,6 +465,8 @@ def main():
     ap.add_argument("--drop-rate", type=float, default=0.3)
     ap.add_argument("--parallel", default=os.environ.get("SGS_PARALLEL", "shard"), choices=["shard", "dp"],
                     help="N > 1: shard ONE graph by destination range (strong scaling) or one graph per rank (weak)")
+    ap.add_argument("--gate", default="learned", choices=["learned", "natural"],
+                    help="learned: every step takes the learned-wins branch (full work); natural: the reference's gate")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

@@ -128,6 +128,8 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
         _check_sampler(host[16:24], q)
         _check_sampler(host[24:32], q)
         update_edge_mlp = bool(host[32] > host[33])
+        if getattr(args, "force_branch", None) == "learned":   # bench only: always time the full (learned-wins) step
+            update_edge_mlp = True
     if update_edge_mlp:
         loss = ops.fused_loss(learned_out, batch.y, tm_u8, p_s if with_edges else None, g_s if with_edges else None,
                               args.regularizer1_coef, args.consist_reg_coef, bool(args.reg1), bool(args.reg2),

@@ -63,14 +63,17 @@ def shard_by_destination(edge_index, num_nodes, world, rank):
 class CudaTopQOps:
     """Local steps of the select, backed by libsgs_b200 (see include/sgs_b200.h K2)."""
 
-    def __init__(self):
+    def __init__(self, persistent=False):
+        """persistent: keep the key / compaction scratch in per-process arenas (one select in flight at a time,
+        as in the sharded training step) instead of allocating it per call."""
         from . import _lib, ops
         self._lib, self._ops = _lib, ops
+        self._persistent = persistent
 
     def keys(self, p, prob, noise, mode, coef, S):
         ops, lib = self._ops, self._lib.lib()
         e = p.numel()
-        keys = torch.empty(e, dtype=torch.int32, device=p.device)
+        keys = ops._ws(4 * e, p.device, "topq_keys" if self._persistent else None).view(torch.int32)
         hist = torch.empty(self._lib.TOPQ_BINS, dtype=torch.int64, device=p.device)
         state = torch.empty(8, dtype=torch.int64, device=p.device)
         one_m, c = ops._coefs(coef)
@@ -92,9 +95,9 @@ class CudaTopQOps:
         ops, lib = self._ops, self._lib.lib()
         e = keys.numel()
         cap = int(q_cap if n_expected is None else n_expected)
-        sel = torch.empty(max(cap, 1), dtype=torch.int32, device=keys.device)
+        sel = ops._vec(max(cap, 1), torch.int32, keys.device)
         n_sel = torch.zeros(1, dtype=torch.int64, device=keys.device)
-        ws = ops._ws(lib.sgs_topq_workspace_bytes(e), keys.device)
+        ws = ops._ws(lib.sgs_topq_workspace_bytes(e), keys.device, "topq_ws" if self._persistent else None)
         self._lib.check(lib.sgs_topq_compact(ops._p(keys), e, ops._p(state), int(tie_skip), ops._p(sel), cap,
                                              None, ops._p(n_sel), ops._p(ws), ws.numel(), ops._stream()),
                         "sgs_topq_compact")
@@ -139,7 +142,11 @@ class DistributedTopQ:
 
     def global_sum(self, p):
         """S = sum over all ranks of p, accumulated in fp64 and rounded once (identical on every rank)."""
-        s = p.sum(dtype=torch.float64).reshape(1)
+        if p.is_cuda:      # fp64-accumulating device reduction without a [E] fp64 temporary
+            from . import ops
+            s = ops.sum_f64(p)
+        else:
+            s = p.sum(dtype=torch.float64).reshape(1)
         self._allreduce(s)
         return s.to(torch.float32)
 
@@ -198,7 +205,11 @@ class DistributedTopQ:
         else:
             # fp32 keys collide routinely at 10^8 edges: n_eq is a handful.  All-gather the tied global ids
             # (padded to n_eq) and cut at the take-th smallest -- one collective, one more host read.
-            tied = gid[torch.nonzero(keys == (tau_bits & 0x7FFFFFFF)).flatten()]
+            eq = keys == (tau_bits & 0x7FFFFFFF)
+            try:      # the local tie count is already on the host: fixed-size nonzero, no extra sync
+                tied = gid[torch.nonzero_static(eq, size=c_r).flatten()]
+            except (RuntimeError, NotImplementedError, AttributeError):
+                tied = gid[torch.nonzero(eq).flatten()]
             if n_eq <= self.TIE_GATHER_MAX:
                 world = dist.get_world_size(self.group)
                 mine = torch.full((n_eq,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=tied.device)

@@ -72,8 +72,39 @@ def _req(t, dtype, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _ws(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+_scratch = {}
+
+
+def _ws(nbytes, device, name=None):
+    """Workspace for one C-ABI call.  With `name`, a persistent per-purpose arena that only ever grows (x1.25):
+    the multi-GB scratch buffers of the scorer / CSR build / sampler then never go back through the caching
+    allocator, whose best-fit reuse breaks down (cudaMalloc + cudaFree stalls inside the step) as soon as the
+    request sizes wobble from step to step, e.g. with the per-rank edge counts of a sharded graph."""
+    nbytes = max(int(nbytes), 256)
+    if name is None:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (name, str(device))
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch.pop(key, None)
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf[:nbytes]
+
+
+_VEC_QUANTUM = 1 << 20
+
+
+def _vec(n, dtype, device, zero=False):
+    """1-D result buffer of n elements whose allocation is rounded up to a 1 Mi-element quantum, so that vectors
+    whose length follows a sampled edge count hit the same cached blocks every step."""
+    n = int(n)
+    cap = max(n, 1)
+    if cap > _VEC_QUANTUM:
+        cap = (cap + _VEC_QUANTUM - 1) // _VEC_QUANTUM * _VEC_QUANTUM
+    buf = (torch.zeros if zero else torch.empty)(cap, dtype=dtype, device=device)
+    return buf[:n]
 
 
 # optional per-kernel-family CUDA-event timing (bench.py's roofline leg); off by default
@@ -134,19 +165,21 @@ class GcnNorm:
         self.deg = torch.empty(n, dtype=torch.float32, device=dev)
         self.dis = torch.empty_like(self.deg)
         self.loopw = torch.empty_like(self.deg)
-        self.what_dst = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        self.what_dst = _vec(max(m, 1), torch.float32, dev)
         check(lib().sgs_gcn_norm(_p(rowptr), _p(perm), _p(nbr), _p(w), m, n, _p(self.deg), _p(self.dis),
                                  _p(self.loopw), _p(self.what_dst), _stream()), "sgs_gcn_norm")
         self._what_src = None
-        self._graph = graph
+        self._graph = weakref.ref(graph)   # weak: graph -> norm -> graph would only be freed by the cyclic GC
         self._w = w
 
     @property
     def what_src(self):
         if self._what_src is None:
-            g = self._graph
+            g = self._graph()
+            if g is None:
+                raise RuntimeError("the graph of this gcn_norm has been released")
             rowptr, perm, nbr, _ = g.csr_src
-            self._what_src = torch.empty(max(g.num_edges, 1), dtype=torch.float32, device=g.device)
+            self._what_src = _vec(max(g.num_edges, 1), torch.float32, g.device)
             check(lib().sgs_gcn_norm_apply(_p(rowptr), _p(perm), _p(nbr), _p(self._w), _p(self.dis),
                                            g.num_edges, g.num_nodes, _p(self._what_src), _stream()),
                   "sgs_gcn_norm_apply")
@@ -187,8 +220,8 @@ class Graph:
     def subgraph(self, ids, want_edge_index=False):
         """Edge-induced subgraph on edge ids (int32 [q]); optionally also the int64 [2,q] tensor."""
         q = int(ids.numel())
-        src = torch.empty(q, dtype=torch.int32, device=self.device)
-        dst = torch.empty_like(src)
+        src = _vec(q, torch.int32, self.device)
+        dst = _vec(q, torch.int32, self.device)
         out = torch.empty(2, q, dtype=torch.int64, device=self.device) if want_edge_index else None
         if self.edge_index is not None:
             check(lib().sgs_edge_index_gather(_p(self.edge_index), self.num_edges, _p(ids), q, _p(out), _p(src),
@@ -203,11 +236,11 @@ class Graph:
     def _build(self, key, other):
         n, m = self.num_nodes, self.num_edges
         rowptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
-        perm = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
-        nbr = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
+        perm = _vec(max(m, 1), torch.int32, self.device)
+        nbr = _vec(max(m, 1), torch.int32, self.device)
         order = torch.empty(n + 1, dtype=torch.int32, device=self.device)   # [N] = number of hub rows
         nbytes = lib().sgs_csr_workspace_bytes(m, n)
-        ws = _ws(nbytes, self.device)
+        ws = _ws(nbytes, self.device, "csr_build")
         with _timed("csr_build"):
             check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(order), _p(ws),
                                       ws.numel(), _stream()), "sgs_csr_build")
@@ -402,8 +435,8 @@ class GCNConvFn(torch.autograd.Function):
                 dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d, precision=PREC_FP32)
         if need_ew and ctx.has_w:
             m = graph.num_edges
-            dew = torch.empty(m, dtype=torch.float32, device=g.device)
-            tmp = torch.empty(2 * m + n, dtype=torch.float32, device=g.device)
+            dew = _vec(m, torch.float32, g.device)
+            tmp = _ws(4 * (2 * m + n), g.device, "edge_grad_tmp").view(torch.float32)
             rp_d, pm_d, nb_d, od_d = graph.csr_dst
             rp_s, pm_s, _, _ = graph.csr_src
             with _timed(f"edge_grad_d{d}"):
@@ -429,9 +462,9 @@ def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0,
     out = _req(out, torch.float32, "out")
     n_nodes, h = out.shape
     n = graph.num_edges if ids is None else int(ids.numel())
-    p = torch.empty(n, dtype=torch.float32, device=out.device)
+    p = _vec(n, torch.float32, out.device)
     nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, prec, 0)
-    ws = _ws(nbytes, out.device)
+    ws = _ws(nbytes, out.device, "edge_score_fwd")
     with _timed("edge_score_fwd"):
         check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
                                        _p(b1), _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(ws), ws.numel(),
@@ -473,7 +506,7 @@ class EdgeScoreFn(torch.autograd.Function):
         dw1 = torch.zeros_like(w1)
         small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
         nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, ctx.prec, 1)
-        ws = _ws(nbytes, dev)
+        ws = _ws(nbytes, dev, "edge_score_bwd")
         with _timed("edge_score_bwd"):
             check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
                                            _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(p_fwd),
@@ -498,6 +531,16 @@ def sum_f32(p):
     ws = _ws(8192, p.device)
     check(lib().sgs_sum_f32(_p(p), p.numel(), _p(s), _p(ws), ws.numel(), _stream()), "sgs_sum_f32")
     return s
+
+
+def sum_f64(p):
+    """sum(p) as a device float64 [1]: the fp64 block partials of sgs_sum_f32 (1024 doubles) summed in fp64 -- the
+    multi-GPU sampler all-reduces this before rounding once to fp32 (no [E] fp64 temporary)."""
+    p = _req(p, torch.float32, "p")
+    s = torch.empty(1, dtype=torch.float32, device=p.device)
+    ws = _ws(8192, p.device)
+    check(lib().sgs_sum_f32(_p(p), p.numel(), _p(s), _p(ws), ws.numel(), _stream()), "sgs_sum_f32")
+    return ws.view(torch.float64)[:1024].sum().reshape(1)
 
 
 def softmax_f32(x):
@@ -566,12 +609,12 @@ def sample_topq(p, prob, q, mode=SAMPLE_TRAIN, coef=0.3, noise=None, S=None, wan
     if mode != SAMPLE_RAW and S is None:
         S = sum_f32(p)
     one_m, c = _coefs(coef)
-    keys = torch.empty(e, dtype=torch.int32, device=dev)
-    sel = torch.empty(q, dtype=torch.int32, device=dev)
+    keys = _ws(4 * e, dev, "topq_keys").view(torch.int32)
+    sel = _vec(q, torch.int32, dev)
     mask = torch.empty(e, dtype=torch.uint8, device=dev) if want_mask else None
     state = torch.empty(8, dtype=torch.int64, device=dev)
     nbytes = lib().sgs_topq_workspace_bytes(e) + _lib.TOPQ_BINS * 8
-    ws = _ws(nbytes, dev)
+    ws = _ws(nbytes, dev, "topq_ws")
     with _timed("sample_topq"):
         check(lib().sgs_sample_topq(_p(p), _p(prob), _p(noise), e, q, one_m, c, mode, _p(S), _p(keys), _p(sel),
                                     _p(mask), _p(state), _p(ws), ws.numel(), _stream()), "sgs_sample_topq")
@@ -585,8 +628,8 @@ def sample_topq(p, prob, q, mode=SAMPLE_TRAIN, coef=0.3, noise=None, S=None, wan
 def gather_selected(p, prob, sel, mode, coef, S, straight_through=False):
     q = sel.numel()
     one_m, c = _coefs(coef)
-    p_sel = torch.empty(q, dtype=torch.float32, device=p.device)
-    w_st = torch.empty_like(p_sel) if straight_through else None
+    p_sel = _vec(q, torch.float32, p.device)
+    w_st = _vec(q, torch.float32, p.device) if straight_through else None
     check(lib().sgs_gather_selected(_p(p), _p(prob), _p(sel), q, one_m, c, mode, _p(S), _p(p_sel), _p(w_st),
                                     _stream()), "sgs_gather_selected")
     return p_sel, w_st
@@ -686,7 +729,7 @@ class FusedLossFn(torch.autograd.Function):
         sub = ctx.sub
         g = g.reshape(1).to(torch.float32).contiguous()
         dlogits = torch.empty_like(logits)
-        dp = torch.empty_like(p_s) if ctx.with_edges else None
+        dp = _vec(p_s.numel(), torch.float32, p_s.device) if ctx.with_edges else None
         q = sub.num_edges if ctx.with_edges else 0
         with _timed("loss_bwd"):
           check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(rm), _p(sub.src) if ctx.with_edges else None,

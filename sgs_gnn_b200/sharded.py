@@ -24,6 +24,7 @@ slab only.  Reference call sites: training_hybrid.py:39-147, model.py:102-122,15
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -162,7 +163,7 @@ class ShardedNorm:
         deg = torch.empty(n, dtype=torch.float32, device=dev)
         dis = torch.empty_like(deg)
         loopw = torch.empty_like(deg)
-        self.what_dst = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        self.what_dst = ops._vec(max(m, 1), torch.float32, dev)
         check(lib().sgs_gcn_norm(_p(rowptr), _p(perm), _p(nbr), _p(w), m, n, _p(deg), _p(dis), _p(loopw),
                                  _p(self.what_dst), _stream()), "sgs_gcn_norm")
         if lg.comm.world > 1:
@@ -173,14 +174,17 @@ class ShardedNorm:
                                            _stream()), "sgs_gcn_norm_apply")
         self.deg, self.dis, self.loopw = deg, dis, loopw
         self._what_src = None
-        self._lg, self._w = lg, w
+        self._lg, self._w = weakref.ref(lg), w   # weak: lg -> norm -> lg would only be freed by the cyclic GC
 
     @property
     def what_src(self):
         if self._what_src is None:
-            g = self._lg.graph
+            lg = self._lg()
+            if lg is None:
+                raise RuntimeError("the graph of this gcn_norm has been released")
+            g = lg.graph
             rowptr, perm, nbr, _ = g.csr_src
-            self._what_src = torch.empty(max(g.num_edges, 1), dtype=torch.float32, device=g.device)
+            self._what_src = ops._vec(max(g.num_edges, 1), torch.float32, g.device)
             check(lib().sgs_gcn_norm_apply(_p(rowptr), _p(perm), _p(nbr), _p(self._w), _p(self.dis), g.num_edges,
                                            g.num_nodes, _p(self._what_src), _stream()), "sgs_gcn_norm_apply")
         return self._what_src
@@ -332,8 +336,9 @@ class ShardedGCNConvFn(torch.autograd.Function):
                     ops.gemm(dh_slab, d, 1, weight, 1, fin, ns, fin, d, out=dx[lo:hi], precision=PREC_FP32)
         if need_ew and ctx.has_w:
             m = g.num_edges
-            dew = torch.zeros(max(m, 1), dtype=torch.float32, device=gout.device)[:m]
-            tmp = torch.zeros(2 * m + n, dtype=torch.float32, device=gout.device)
+            dew = ops._vec(m, torch.float32, gout.device, zero=True)
+            tmp = ops._ws(4 * (2 * m + n), gout.device, "edge_grad_tmp").view(torch.float32)
+            tmp.zero_()
             rp_d, pm_d, nb_d, od_d = g.csr_dst
             rp_s, pm_s, _, _ = g.csr_src
             with _timed(f"edge_grad_d{d}"):
@@ -422,7 +427,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
     dev = sb.x.device
     scorer = model.edge_prob_mlp
     coef = args.degree_bias_coef
-    topq = sdist.DistributedTopQ(group=comm.group)
+    topq = sdist.DistributedTopQ(sdist.CudaTopQOps(persistent=True), group=comm.group)
     e_loc = g_loc.num_edges
     tm_owned = sb.train_mask_owned.view(torch.uint8)    # CE / accuracy rows: train AND owned
     tm_full = sb.train_mask.view(torch.uint8)           # reg1 validity tests both endpoints on the full mask
@@ -479,6 +484,8 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
     host = torch.cat([acc[2:3], acc[10:11]]).cpu()
     if args.conditional:
         update_edge_mlp = bool(host[0] > host[1])
+        if getattr(args, "force_branch", None) == "learned":   # bench only: always time the full (learned-wins) step
+            update_edge_mlp = True
     if update_edge_mlp:
         loss = ops.fused_loss(learned_out, sb.y, tm_full, p_s if with_edges else None,
                               lg_s.graph if with_edges else None, args.regularizer1_coef, args.consist_reg_coef,
