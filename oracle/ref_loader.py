@@ -18,7 +18,7 @@ REFERENCE_DIR = os.environ.get("SGS_REFERENCE_DIR", "/root/reference")
 SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 
 _REF_MODULES = ("sampling", "utils", "model", "training_hybrid",
-                "training_straight_through", "training_two_pass", "training")
+                "training_straight_through", "training_two_pass", "training", "evaluate")
 _SHIM_ROOTS = ("torch_geometric", "matplotlib")
 _cache = None
 

@@ -100,6 +100,11 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
         # edge_probs_full[mask] with grad (training_hybrid.py:86): backward over the q edges only
         p_sel = ops.gather_selected(p_full, None, smp.sel, ops.SAMPLE_RAW, 0.0, None)[0]
         p_s = scorer.score(out, g_full, ids=smp.sel, precomputed=p_sel, seed=seed_sc)
+    elif pipeline == "two_pass":
+        # pass 3 (training_two_pass.py:75-81): the scorer runs again on the sampled subgraph itself -- message
+        # passing over the q sampled edges, scoring of those q edges, fresh dropout masks, gradients enabled
+        out2 = scorer.embed(batch.x, g_s)
+        p_s = scorer.score(out2, g_s)
     elif pipeline == "straight_through":
         # sampled_edge_weight = (p * st)[mask].clamp(0,1) with dense gradient
         # (training_straight_through.py:60-75, sampling.py:137-155)

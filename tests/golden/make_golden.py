@@ -145,7 +145,8 @@ def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     args = make_args(pipeline=pipeline)
     crit = nn.CrossEntropyLoss()
-    mod = ref.training_hybrid if pipeline == "hybrid" else ref.training_straight_through
+    mod = {"hybrid": ref.training_hybrid, "straight_through": ref.training_straight_through,
+           "two_pass": ref.training_two_pass}[pipeline]
     losses, branch, noises = [], [], []
     for ep in range(epochs):
         torch.manual_seed(1000 + ep)
@@ -168,9 +169,47 @@ def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
         **{"sd0." + k: v for k, v in sd0.items()}, **{"sd1." + k: v for k, v in sd1.items()})
 
 
+def golden_eval():
+    """evaluate.evaluate / evaluate.ensemble_evaluate (learned mode) on a model in eval mode; the Exp(1) noise
+    torch.multinomial draws for each ensemble member is re-generated from the same seed and stored."""
+    n, e, f, c, h, members = 500, 5000, 16, 4, 32, 3
+    b = synth.make_graph(None, seed=51, n=n, e=e, f=f, c=c, homophily=0.7)
+    q = int(e * 0.2)
+    model, *_ = build_ref_model(f, h, c, 0.3, 52)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    args = make_args(num_samples_eval=members)
+    torch.manual_seed(77)
+    f1_ens = ref.evaluate.ensemble_evaluate(args, model, [b], torch.device("cpu"), q=q, mode="learned")
+    torch.manual_seed(77)
+    noises = torch.stack([ox.exponential_noise(e) for _ in range(members)])
+    torch.manual_seed(78)
+    f1_one = ref.evaluate.evaluate(args, model, [b], torch.device("cpu"), q=q, mode="learned")
+    torch.manual_seed(78)
+    noise_one = ox.exponential_noise(e)
+    params = {k: v for k, v in sd.items()}
+    with torch.no_grad():
+        f1_o, mean_logits = ox.ensemble_evaluate(params, b, q, list(noises))
+        f1_o1, logits_one = ox.ensemble_evaluate(params, b, q, [noise_one])
+    assert np.allclose(f1_o, f1_ens) and np.allclose(f1_o1, f1_one), (f1_o, f1_ens, f1_o1, f1_one)
+    print("eval f1 (ensemble, single):", f1_ens, f1_one)
+    npz("eval_small.npz", x=b.x, y=b.y, edge_index=b.edge_index, train_mask=b.train_mask, val_mask=b.val_mask,
+        test_mask=b.test_mask, prob=b.prob, q=q, hidden=h, members=members, noises=noises, noise_one=noise_one,
+        f1_ensemble=np.array(f1_ens), f1_single=np.array(f1_one), mean_logits=mean_logits, logits_single=logits_one,
+        **{"sd." + k: v for k, v in sd.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    golden_sampler()
-    golden_forward()
-    golden_step("hybrid", "hybrid", 300, 2400, 20, 4, 32, 6, 31)
-    golden_step("straight_through", "st", 300, 2400, 20, 4, 32, 6, 41)
+    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval"]
+    if "sampler" in which:
+        golden_sampler()
+    if "forward" in which:
+        golden_forward()
+    if "hybrid" in which:
+        golden_step("hybrid", "hybrid", 300, 2400, 20, 4, 32, 6, 31)
+    if "st" in which:
+        golden_step("straight_through", "st", 300, 2400, 20, 4, 32, 6, 41)
+    if "two_pass" in which:
+        golden_step("two_pass", "two_pass", 300, 2400, 20, 4, 32, 6, 61)
+    if "eval" in which:
+        golden_eval()

@@ -24,7 +24,8 @@ def relerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-@pytest.mark.parametrize("name,pipeline", [("step_hybrid.npz", "hybrid"), ("step_st.npz", "straight_through")])
+@pytest.mark.parametrize("name,pipeline", [("step_hybrid.npz", "hybrid"), ("step_st.npz", "straight_through"),
+                                           ("step_two_pass.npz", "two_pass")])
 def test_epochs_match_reference_training(dev, name, pipeline, monkeypatch):
     from sgs_gnn_b200 import _train_core, sampling, training
     from sgs_gnn_b200.model import GNNModel

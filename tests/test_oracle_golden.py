@@ -64,7 +64,8 @@ def test_losses_match_reference():
 
 
 def test_first_step_matches_reference_training():
-    for name, pipe in (("step_hybrid.npz", "hybrid"), ("step_st.npz", "straight_through")):
+    for name, pipe in (("step_hybrid.npz", "hybrid"), ("step_st.npz", "straight_through"),
+                       ("step_two_pass.npz", "two_pass")):
         z = load_golden(name)
         b = FixtureBatch(z)
         params = {k[4:]: t(v).clone().requires_grad_(True) for k, v in z.items() if k.startswith("sd0.")}
@@ -73,6 +74,24 @@ def test_first_step_matches_reference_training():
         assert abs(st.loss - float(z["losses"][0])) < 1e-5
         assert (st.branch == "learned") == bool(z["learned_wins"][0])
         assert torch.equal(st.sel, t(z["oracle_sel0"]))
+
+
+def test_ensemble_evaluate_matches_reference():
+    """evaluate.py:6-173 (learned mode): the oracle with the reference's own Exp(1) draws injected reproduces the
+    reference's F1 triple, for the 3-member ensemble and for the single-member `evaluate`."""
+    z = load_golden("eval_small.npz")
+
+    class B(FixtureBatch):
+        pass
+
+    b = B(z)
+    b.val_mask, b.test_mask = t(z["val_mask"]), t(z["test_mask"])
+    params = {k[3:]: t(v) for k, v in z.items() if k.startswith("sd.")}
+    with torch.no_grad():
+        f1, mean_logits = ox.ensemble_evaluate(params, b, int(z["q"]), list(t(z["noises"])))
+        f1_one, _ = ox.ensemble_evaluate(params, b, int(z["q"]), [t(z["noise_one"])])
+    assert np.allclose(f1, z["f1_ensemble"]) and np.allclose(f1_one, z["f1_single"])
+    assert torch.allclose(mean_logits, t(z["mean_logits"]), atol=1e-6)
 
 
 def test_edge_weight_grad_formula():
