@@ -109,6 +109,19 @@ def test_edge_weight_grad_formula():
     assert torch.allclose(ga[keep], closed[keep], atol=1e-12)
 
 
+def test_add_degree_dropin_matches_oracle():
+    from types import SimpleNamespace
+    from sgs_gnn_b200 import datasets, synth
+    b = synth.make_graph("amazon-ratings", seed=5, scale=0.2)
+    d = SimpleNamespace(edge_index=b.edge_index, x=b.x, num_nodes=b.num_nodes)
+    datasets.add_degree(d)
+    assert torch.equal(d.prob, ox.degree_prior(b.edge_index, b.num_nodes))
+    d.edge_index = b.edge_index.flip(1)
+    import pytest
+    with pytest.raises(RuntimeError, match="sorted"):
+        datasets.add_degree(d)
+
+
 def test_degree_prior_is_a_distribution():
     from sgs_gnn_b200 import synth
     b = synth.make_graph("smallcora", seed=3)
