@@ -363,10 +363,15 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   const int64_t ntiles = (n + TILE_M - 1) / TILE_M;
   const int64_t tile0 = blockIdx.x / NKIND;
   const int64_t tstep = gridDim.x / NKIND;
+  // Roles: the epilogue (gathers, TMEM reads, segment reduction, REDs) is the long pole of this kernel and the dA
+  // loaders are plain streaming loads, so 8 of the 13 warps drain accumulators: group 0 (warps 0-3) takes this
+  // CTA's even tiles / accumulator 0, group 1 (warps 9-12) the odd ones; warps 5-8 load dA, warp 4 issues MMAs.
+  constexpr int BF_PROD_WARP0 = MMA_WARP + 1, BF_PROD_WARPS = 4, BF_PROD_THREADS = BF_PROD_WARPS * 32;
+  constexpr int BF_EPI1_WARP0 = BF_PROD_WARP0 + BF_PROD_WARPS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(full0 + 8 * s, PROD_THREADS);
+      mbar_init(full0 + 8 * s, BF_PROD_THREADS);
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -406,19 +411,19 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   const uint32_t tmem_base = *tmem_ptr_s;
   const float invS = 1.0f / grad_scale(dp_absmax[0]);
 
-  if (warp >= PROD_WARP0) {
+  if (warp >= BF_PROD_WARP0 && warp < BF_EPI1_WARP0) {
     // ------------------------------- dA loaders: [128 e x 128 j] sub-tiles -------------------------------
-    const int pt = threadIdx.x - PROD_WARP0 * 32;
+    const int pt = threadIdx.x - BF_PROD_WARP0 * 32;
     const int c = pt & 15;          // 16-byte chunk (8 hidden units) inside the 128-unit sub-tile
-    const int row_base = pt >> 4;   // rows row_base + 16*i
+    const int row_base = pt >> 4;   // rows row_base + 8*i
     uint32_t it = 0;
     for (int64_t t = tile0; t < ntiles; t += tstep) {
 #pragma unroll 1
       for (int js = 0; js < NJ; ++js, ++it) {
-        uint4 v[8];
+        uint4 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t row = t * TILE_M + row_base + 16 * i;
+        for (int i = 0; i < 16; ++i) {
+          const int64_t row = t * TILE_M + row_base + 8 * i;
           v[i] = make_uint4(0, 0, 0, 0);
           if (row < n) v[i] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + row * H + js * 128 + c * 8));
         }
@@ -426,10 +431,9 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
         uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<uint4*>(stage + (c >> 3) * (TILE_M * 128) + sw128_offset(row_base + 16 * i, c & 7)) = v[i];
-        fence_proxy_async_smem();
-        mbar_arrive(full0 + 8 * slot);
+        for (int i = 0; i < 16; ++i)
+          *reinterpret_cast<uint4*>(stage + (c >> 3) * (TILE_M * 128) + sw128_offset(row_base + 8 * i, c & 7)) = v[i];
+        mbar_arrive(full0 + 8 * slot);   // the MMA thread issues the proxy fence (see scorer_producer.cuh)
       }
     }
   } else if (warp == MMA_WARP) {
@@ -444,6 +448,7 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         for (int js = 0; js < NJ; ++js, ++it) {
           const uint32_t slot = it % NSTAGE;
           mbar_wait(full0 + 8 * slot, (it / NSTAGE) & 1);
+          fence_proxy_async_smem();   // loaders' generic-proxy stores -> async proxy
           tc_fence_after();
 #pragma unroll
           for (int qd = 0; qd < NQ; ++qd) {
@@ -466,9 +471,9 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     const int lg = warp & 3;
     const int r = lg * 32 + lane;
     const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
-    uint32_t lt = 0;
-    for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
-      const uint32_t tb = lt & 1;
+    const uint32_t grp = warp >= BF_EPI1_WARP0 ? 1u : 0u;
+    for (int64_t t = tile0 + grp * tstep, lt = grp; t < ntiles; t += 2 * tstep, lt += 2) {
+      const uint32_t tb = grp;   // == lt & 1
       const int64_t i = t * TILE_M + r;
       const bool live = i < n;
       int64_t e = live ? i : n - 1;
@@ -477,16 +482,30 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
       const T* xrow = tab + (int64_t)s_node * H;
       const T* yrow = tab + (int64_t)d_node * H;
       float* dyrow = d_out + (int64_t)d_node * H;
+      // the embedding-row slices of slice `part + 1` are in flight while slice `part` is reduced; the first ones
+      // are issued before the accumulator is waited for
+      uint4 nx0, nx1, ny0, ny1;
+      {
+        const int c0 = kind * CB;
+        nx0 = *reinterpret_cast<const uint4*>(xrow + c0);
+        nx1 = *reinterpret_cast<const uint4*>(xrow + c0 + 8);
+        ny0 = *reinterpret_cast<const uint4*>(yrow + c0);
+        ny1 = *reinterpret_cast<const uint4*>(yrow + c0 + 8);
+      }
       mbar_wait(dffull0 + 8 * tb, (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int part = 0; part < NQ * 4; ++part) {
         const int qd = part >> 2, q16 = part & 3;                     // 16-column slice q16 of column group qd
         const int col0 = kind * CB + qd * 64 + q16 * 16;              // 16 node-embedding columns
-        const uint4 xv0 = *reinterpret_cast<const uint4*>(xrow + col0);
-        const uint4 xv1 = *reinterpret_cast<const uint4*>(xrow + col0 + 8);
-        const uint4 yv0 = *reinterpret_cast<const uint4*>(yrow + col0);
-        const uint4 yv1 = *reinterpret_cast<const uint4*>(yrow + col0 + 8);
+        const uint4 xv0 = nx0, xv1 = nx1, yv0 = ny0, yv1 = ny1;
+        if (part + 1 < NQ * 4) {
+          const int cn = kind * CB + ((part + 1) >> 2) * 64 + ((part + 1) & 3) * 16;
+          nx0 = *reinterpret_cast<const uint4*>(xrow + cn);
+          nx1 = *reinterpret_cast<const uint4*>(xrow + cn + 8);
+          ny0 = *reinterpret_cast<const uint4*>(yrow + cn);
+          ny1 = *reinterpret_cast<const uint4*>(yrow + cn + 8);
+        }
         uint32_t f1[16], f2[16];
         tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + q16 * 16, f1);
         tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + 64 + q16 * 16, f2);
