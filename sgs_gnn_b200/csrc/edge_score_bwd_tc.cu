@@ -1,24 +1,39 @@
 // K1b tensor-core backward of the edge scorer: three fused tcgen05 kernels.  Nothing of size [q, 2H] is ever
-// written to HBM; the only intermediate is the 16-bit dA [q, H] (hidden-layer gradient).
+// written to HBM; the only intermediate is the 16-bit gate gradient G [q, H],
+//       G[e, j] = S * dz_e / (1 - p_drop) * [Z_ej + b1_j > 0] * keep_ej ,        dz = dp * p * (1 - p),
+// i.e. the hidden-layer gradient dA = G . diag(w2) WITHOUT its w2 factor.  That factor is folded into operands and
+// final epilogues, so no per-tile epilogue reduces anything across rows:
 //
-//  BA  (per 128-edge tile, per block of BN hidden units; W1 block resident in smem, as the forward):
-//        MMA : Z  = F . W1blk^T                              (recompute)
-//        EPI : dA = S * dz * w2 * keep * [Z + b1 > 0]  -> HBM (16 bit);  dw2, db1, db2 (warp transpose-reduce)
-//  BF  (per 128-edge tile, per block of 128 node-embedding columns; W1[:, cols] resident in smem and read as an
-//       MN-major operand -- the row-major bytes "transposed" by the descriptor):
-//        MMA : dF = dA . W1[:, cols]                          (K = H hidden units)
+//  BA  (recompute; H = 256: the CTA-pair forward kernel in MODE 1, edge_score_tc2.cu; H = 128: the kernel below)
+//        MMA : Z  = F . W1^T ;   EPI : G -> HBM (16 bit), db2 += sum dz
+//  BF  (per 128-edge tile, per block of 128 node-embedding columns; diag(w2) . W1[:, cols] resident in smem and read
+//       as an MN-major operand -- the row-major bytes "transposed" by the descriptor):
+//        MMA : dF = G . (diag(w2) W1)[:, cols]                 (K = H hidden units)
 //        EPI : d_out[src] += dF1*y + dF2  (segment-reduced over equal-src rows of a warp, then one coalesced RED)
 //              d_out[dst] += dF1*x - dF2  (128-bit vector RED)
-//  BW  dW1blk[BN, 2H] += dA^T . F : both operands are edge-major tiles read as MN-major; the [BN x 2H] fp32
-//        accumulator stays in TMEM (512 columns) for the whole kernel.
+//  BW  P[BN, 2H] = G^T . F : both operands are edge-major tiles read as MN-major; the [BN x 2H] fp32 accumulator
+//        stays in TMEM (512 columns) for the whole kernel; the loaders also keep per-column sums g_j = sum_e G[e, j].
+//        Final epilogue (once per CTA), all from P and g:
+//              dW1[j, :] += w2_j * P[j, :] / S
+//              db1[j]    += w2_j * g_j / S
+//              dw2[j]    += ( W1[j, :] . P[j, :] + b1_j * g_j ) / S
+//        The last line is  sum_e dz_e * keep * relu(Z_ej + b1_j) / (1 - p)  rewritten with Z = F . W1^T: the hidden
+//        activations never have to meet dz in a per-tile reduction.
 //
-// dz = dp * p * (1 - p) uses the forward probability saved by the caller.  S = 2^k (from max|dp|) keeps fp16 dA
-// in range; it is divided out again in the epilogues.
+// S = 2^k (from max|dp|) keeps fp16 G in range; it is divided out again in the epilogues.
 #include "common.cuh"
 #include "tc.cuh"
 #include "scorer_producer.cuh"
 
+#include <type_traits>
+
 namespace sgs {
+
+int32_t edge_score_bwd_gate_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, float p_drop,
+                                 uint64_t seed, const float* p_fwd, const float* dp, const float* dp_absmax,
+                                 void* g_out, float* db2, cudaStream_t st);
+
 
 namespace kb {
 constexpr int TILE_M = 128;
@@ -35,22 +50,8 @@ constexpr int BW_MMA_WARP = 8;
 constexpr int BW_THREADS = 17 * 32;
 }  // namespace kb
 
-// in-warp transpose-reduce: every lane holds v[0..31] (one row, 32 columns); on return lane L holds the sum over
-// the 32 lanes (rows) of column L.  31 shuffles (recursive halving).
-__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool upper = (lane & half) != 0;
-#pragma unroll
-    for (int j = 0; j < half; ++j) {
-      const float send = upper ? v[j] : v[j + half];
-      const float keep = upper ? v[j + half] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
-  }
-  return v[0];
-}
-// 16 columns per lane: lanes L and L^16 both end with the sum over all 32 rows of column (L & 15).
+// in-warp transpose-reduce (recursive halving): every lane holds v[0..15] (one row, 16 columns); on return lanes L
+// and L^16 both hold the sum over all 32 rows of column (L & 15).
 __device__ __forceinline__ float warp_colsum16(float* v, int lane) {
 #pragma unroll
   for (int half = 8; half >= 1; half >>= 1) {
@@ -72,11 +73,6 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
-}
-
-__device__ __forceinline__ float grad_scale(float absmax) {
-  if (!(absmax > 0.f) || isinf(absmax)) return 1.0f;
-  return exp2f(floorf(log2f(1024.0f / absmax)));
 }
 
 template <typename T>
@@ -102,10 +98,9 @@ template <typename T, int BN, int H>
 __global__ void __launch_bounds__(kb::THREADS, 1)
 edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
-                         const float* __restrict__ b1, const float* __restrict__ w2, float p_drop, uint64_t seed,
+                         const float* __restrict__ b1, float p_drop, uint64_t seed,
                          const float* __restrict__ p_fwd, const float* __restrict__ dp,
-                         const float* __restrict__ dp_absmax, T* __restrict__ dA_out, float* __restrict__ dw2,
-                         float* __restrict__ db1, float* __restrict__ db2) {
+                         const float* __restrict__ dp_absmax, T* __restrict__ g_out, float* __restrict__ db2) {
   using namespace kb;
   using namespace tc;
   constexpr int NB = H / BN;
@@ -130,8 +125,7 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   const uint32_t b_base = sm_addr;
   const uint32_t a_base = b_base + B_BYTES;
   float* b1s = reinterpret_cast<float*>(sm + B_BYTES + NSTAGE * STAGE_BYTES);
-  float* w2s = b1s + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w2s + BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + 2 * BN);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t full0 = bar0, empty0 = bar0 + 32, zfull0 = bar0 + 64, zempty0 = bar0 + 80;
@@ -176,17 +170,12 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     o.w = Cvt<T>::pack(b.z, b.w);
     *reinterpret_cast<uint4*>(sm + (2 * sp + half) * B_BLOCK_BYTES + sw128_offset(nrow, c16)) = o;
   }
-  for (int j = threadIdx.x; j < BN; j += THREADS) {
-    b1s[j] = b1[nb * BN + j];
-    w2s[j] = w2[nb * BN + j];
-  }
+  for (int j = threadIdx.x; j < BN; j += THREADS) b1s[j] = b1[nb * BN + j];
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  const float S = grad_scale(dp_absmax[0]);
-  const float invS = 1.0f / S;
 
   if (warp >= PROD_WARP0) {
     // ------------------------------- producers (as the forward) -------------------------------
@@ -223,17 +212,13 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     }
     __syncwarp();
   } else {
-    // ------------------------------- epilogue: Z -> dA, parameter gradients -------------------------------
-    const int lg = warp & 3;
-    constexpr int ch = 0;           // one epilogue warp per TMEM lane quarter handles all BN columns
-    constexpr int CW = BN;
+    // ------------------------------- epilogue: Z -> G (16 bit), db2 -------------------------------
+    const int lg = warp & 3;        // one epilogue warp per TMEM lane quarter handles all BN columns
     const int r = lg * 32 + lane;
-    const uint32_t thr = dropout_threshold(p_drop);
+    const uint32_t thr32 = dropout_threshold32(dropout_threshold(p_drop));
     const bool drop = p_drop > 0.f;
-    const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
-    float acc_w2[CW / 32], acc_b1[CW / 32], acc_b2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < CW / 32; ++k) acc_w2[k] = acc_b1[k] = 0.f;
+    const float gscale = grad_scale(dp_absmax[0]) * (drop ? 1.0f / (1.0f - p_drop) : 1.0f);
+    float acc_b2 = 0.f;
     const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
     uint32_t lt = 0;
     for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
@@ -247,66 +232,49 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         dz = dp[i] * pe * (1.0f - pe);
         if (drop) rowkey = dropout_rowkey(seed, (uint64_t)(ids ? ids[i] : i));
       }
-      if (ch == 0) acc_b2 += dz;
-      const float dzs = dz * S;
+      acc_b2 += dz;
+      const float g = dz * gscale;
+      const uint32_t gg = Cvt<T>::pack(g, g);
+      const uint32_t g_lo = gg & 0xFFFFu, g_hi = gg & 0xFFFF0000u;
       mbar_wait(zfull0 + 8 * acc, (lt >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < CW; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + acc * BN + ch * CW + c0, v);
+        tmem_ld32(tmem_base + lane_off + acc * BN + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= CW) {  // accumulator fully read
+        if (c0 + 32 >= BN) {  // accumulator fully read
           tc_fence_before();
           mbar_arrive(zempty0 + 8 * acc);
         }
-        float hw[32], da[32];
+        uint32_t o[16];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const int col = ch * CW + c0 + j4 * 4;
-          const float4 bb = *reinterpret_cast<const float4*>(b1s + col);
-          const float4 ww = *reinterpret_cast<const float4*>(w2s + col);
-          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-          const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
-          uint32_t r0 = 0xFFFFFFFFu, r1 = 0xFFFFFFFFu;
+          const float4 bb = *reinterpret_cast<const float4*>(b1s + c0 + j4 * 4);
+          bool m0 = __uint_as_float(v[j4 * 4 + 0]) + bb.x > 0.f;
+          bool m1 = __uint_as_float(v[j4 * 4 + 1]) + bb.y > 0.f;
+          bool m2 = __uint_as_float(v[j4 * 4 + 2]) + bb.z > 0.f;
+          bool m3 = __uint_as_float(v[j4 * 4 + 3]) + bb.w > 0.f;
           if (drop) {
-            const uint32_t cp = (uint32_t)(nb * BN + col) >> 1;
-            r0 = dropout_pair(rowkey, cp);
-            r1 = dropout_pair(rowkey, cp + 1);
+            const uint32_t cp = (uint32_t)(nb * BN + c0 + j4 * 4) >> 1;
+            const uint32_t xa = rowkey ^ dropout_colmix(cp);
+            const uint32_t xb = rowkey ^ dropout_colmix(cp + 1);
+            m0 = m0 && (xa * kDropMulEven >= thr32);
+            m1 = m1 && (xa * kDropMulOdd >= thr32);
+            m2 = m2 && (xb * kDropMulEven >= thr32);
+            m3 = m3 && (xb * kDropMulOdd >= thr32);
           }
-          const bool keep[4] = {(r0 & 0xFFFFu) >= thr, (r0 >> 16) >= thr, (r1 & 0xFFFFu) >= thr, (r1 >> 16) >= thr};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float pre = __uint_as_float(v[j4 * 4 + k]) + bv[k];
-            const float m = (pre > 0.f && (!drop || keep[k])) ? scale : 0.f;
-            hw[j4 * 4 + k] = dz * (pre * m);       // dz * hidden  -> dw2
-            da[j4 * 4 + k] = dzs * wv[k] * m;      // scaled dA
-          }
+          o[2 * j4] = (m0 ? g_lo : 0u) | (m1 ? g_hi : 0u);
+          o[2 * j4 + 1] = (m2 ? g_lo : 0u) | (m3 ? g_hi : 0u);
         }
         if (live) {
+          uint4* gp = reinterpret_cast<uint4*>(g_out + i * H + nb * BN + c0);
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            uint4 o;
-            o.x = Cvt<T>::pack(da[c8 * 8 + 0], da[c8 * 8 + 1]);
-            o.y = Cvt<T>::pack(da[c8 * 8 + 2], da[c8 * 8 + 3]);
-            o.z = Cvt<T>::pack(da[c8 * 8 + 4], da[c8 * 8 + 5]);
-            o.w = Cvt<T>::pack(da[c8 * 8 + 6], da[c8 * 8 + 7]);
-            *reinterpret_cast<uint4*>(dA_out + i * H + nb * BN + ch * CW + c0 + c8 * 8) = o;
-          }
+          for (int c8 = 0; c8 < 4; ++c8) gp[c8] = make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) da[j] *= invS;
-        acc_w2[c0 / 32] += warp_colsum32(hw, lane);
-        acc_b1[c0 / 32] += warp_colsum32(da, lane);
       }
     }
-#pragma unroll
-    for (int k = 0; k < CW / 32; ++k) {
-      const int col = nb * BN + ch * CW + 32 * k + lane;
-      atomicAdd(dw2 + col, acc_w2[k]);
-      atomicAdd(db1 + col, acc_b1[k]);
-    }
-    if (nb == 0 && ch == 0) {
+    if (nb == 0) {
       acc_b2 = warp_sum(acc_b2);
       if (lane == 0) atomicAdd(db2, acc_b2);
     }
@@ -321,13 +289,14 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 }
 
 // =============================================================================================
-// BF: dF = dA . W1[:, column block]  and the scatter into d_out
+// BF: dF = G . (diag(w2) W1)[:, column block]  and the scatter into d_out
 // =============================================================================================
 template <typename T, int H>
 __global__ void __launch_bounds__(kb::THREADS, 1)
 edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
-                         const T* __restrict__ dA, const float* __restrict__ dp_absmax, float* __restrict__ d_out) {
+                         const float* __restrict__ w2, const T* __restrict__ dA, const float* __restrict__ dp_absmax,
+                         float* __restrict__ d_out) {
   using namespace kb;
   using namespace tc;
   constexpr int CB = 128;                       // node-embedding columns per CTA kind
@@ -384,7 +353,7 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     tmem_alloc(smem_u32(tmem_ptr_s), 512);
     tmem_relinquish();
   }
-  // resident operand: rows j = 0..H-1 of W1, this kind's columns, as blocks [H x 64]:
+  // resident operand: rows j = 0..H-1 of diag(w2) . W1, this kind's columns, as blocks [H x 64]:
   //   block 2*qd   : product-part columns    kind*CB + 64*qd + [0,64)
   //   block 2*qd+1 : difference-part columns H + kind*CB + 64*qd + [0,64)
   for (int idx = threadIdx.x; idx < H * (2 * CB / 8); idx += THREADS) {
@@ -395,13 +364,14 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     const int c16 = kc & 7;
     const int kcol = (half ? H : 0) + kind * CB + qd * 64 + c16 * 8;
     const float* g = W1 + (int64_t)j * (2 * H) + kcol;
+    const float wj = w2[j];
     const float4 a = *reinterpret_cast<const float4*>(g);
     const float4 b = *reinterpret_cast<const float4*>(g + 4);
     uint4 o;
-    o.x = Cvt<T>::pack(a.x, a.y);
-    o.y = Cvt<T>::pack(a.z, a.w);
-    o.z = Cvt<T>::pack(b.x, b.y);
-    o.w = Cvt<T>::pack(b.z, b.w);
+    o.x = Cvt<T>::pack(wj * a.x, wj * a.y);
+    o.y = Cvt<T>::pack(wj * a.z, wj * a.w);
+    o.z = Cvt<T>::pack(wj * b.x, wj * b.y);
+    o.w = Cvt<T>::pack(wj * b.z, wj * b.w);
     *reinterpret_cast<uint4*>(sm + blk * BLK + sw128_offset(j, c16)) = o;
   }
   fence_proxy_async_smem();
@@ -570,13 +540,15 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 }
 
 // =============================================================================================
-// BW: dW1blk[BN, 2H] += dA^T . F   over all edges of this CTA's tiles
+// BW: P[BN, 2H] = G^T . F over all edges of this CTA's tiles, g = column sums of G;  dW1, db1, dw2 from P and g
 // =============================================================================================
 template <typename T, int BN, int H>
 __global__ void __launch_bounds__(kb::BW_THREADS, 1)
 edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const T* __restrict__ dA,
-                         const float* __restrict__ dp_absmax, float* __restrict__ dW1) {
+                         const float* __restrict__ dp_absmax, const float* __restrict__ W1,
+                         const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ dW1,
+                         float* __restrict__ db1, float* __restrict__ dw2) {
   using namespace kb;
   using namespace tc;
   constexpr int NB = H / BN;
@@ -597,10 +569,11 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   {
     uint32_t dyn_size;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
-    if (pad + NSTAGE * STAGE + 128 > dyn_size) __trap();
+    if (pad + NSTAGE * STAGE + 128 + BN * 4 > dyn_size) __trap();
   }
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + NSTAGE * STAGE);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 8);
+  float* gsum_s = reinterpret_cast<float*>(sm + NSTAGE * STAGE + 128);   // [BN] column sums of G
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 16, done_bar = full0 + 32;
 
   const int warp = threadIdx.x >> 5;
@@ -619,6 +592,7 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
+  for (int j = threadIdx.x; j < BN; j += BW_THREADS) gsum_s[j] = 0.f;
   if (warp == BW_MMA_WARP) {
     tmem_alloc(smem_u32(tmem_ptr_s), TMEM_ALLOC);
     tmem_relinquish();
@@ -660,6 +634,11 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     constexpr int NIT = SUB_M * CH / LOAD_THREADS;       // F items per thread and stage
     constexpr int NDA = SUB_M * (BN / 8) / LOAD_THREADS; // dA items per thread and stage
     static_assert(SUB_M * CH % LOAD_THREADS == 0 && SUB_M * (BN / 8) % LOAD_THREADS == 0, "loader mapping");
+    // every G item of a thread is the same 16-byte chunk (8 hidden units) of some row: LOAD_THREADS % (BN / 8) == 0
+    static_assert(LOAD_THREADS % (BN / 8) == 0, "column-sum mapping");
+    float gs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gs[k] = 0.f;
     uint32_t it = 0;
     for (int64_t s = sub0; s < nsub; s += sstep, ++it) {
       // all global loads of the stage are issued before the stage slot is waited for
@@ -717,14 +696,35 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
       }
       fence_proxy_async_smem();
       mbar_arrive(full0 + 8 * slot);
+#pragma unroll
+      for (int k = 0; k < NDA; ++k) {
+        const uint32_t w[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float2 f = Cvt<T>::unpack(w[m]);
+          gs[2 * m] += f.x;
+          gs[2 * m + 1] += f.y;
+        }
+      }
     }
-    // ---- final epilogue: accumulator -> dW1 (original column order), unscaled ----
+    {
+      const int cc = lt_id % (BN / 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(gsum_s + cc * 8 + k, gs[k]);
+    }
+    // all loader warps (everything but the MMA warp) have added their column sums
+    asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");
+    // ---- final epilogue: P, g -> dW1 (original column order), db1, dw2; the scale S divided out ----
     if (warp < 4) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const float invS = 1.0f / grad_scale(dp_absmax[0]);
       const int jrow = warp * 32 + lane;   // TMEM lane == hidden unit inside the block
-      float* wrow = dW1 + (int64_t)(nb * BN + jrow) * (2 * H);
+      const int j = nb * BN + jrow;
+      const float wj = w2[j] * invS;
+      const float* w1row = W1 + (int64_t)j * (2 * H);
+      float* wrow = dW1 + (int64_t)j * (2 * H);
+      float dot = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < NCOLS; c0 += 32) {
         uint32_t v[32];
@@ -734,10 +734,17 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         const int b = c0 >> 6;
         const int kcol = ((b & 1) ? H : 0) + (b >> 1) * 64 + (c0 & 63);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          red_add_v4(wrow + kcol + j, __uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
-                     __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS);
+        for (int k = 0; k < 32; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(w1row + kcol + k);
+          const float p0 = __uint_as_float(v[k]), p1 = __uint_as_float(v[k + 1]);
+          const float p2 = __uint_as_float(v[k + 2]), p3 = __uint_as_float(v[k + 3]);
+          dot = fmaf(w.x, p0, fmaf(w.y, p1, fmaf(w.z, p2, fmaf(w.w, p3, dot))));
+          red_add_v4(wrow + kcol + k, p0 * wj, p1 * wj, p2 * wj, p3 * wj);
+        }
       }
+      const float gj = gsum_s[jrow];
+      atomicAdd(db1 + j, wj * gj);
+      atomicAdd(dw2 + j, (dot + b1[j] * gj) * invS);
     }
   }
   tc_fence_before();
@@ -785,13 +792,18 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     if (gr > items * kinds) gr = items * kinds;
     return (unsigned)gr;
   };
-  {
+  if (H == 256 && n >= 2 * kb::TILE_M) {
+    // CTA pairs: every edge tile is gathered and built once (edge_score_tc2.cu, MODE 1)
+    const int32_t rc = edge_score_bwd_gate_pair(tab, std::is_same<T, __nv_bfloat16>::value ? 1 : 0, src, dst, ids, n,
+                                                W1, b1, p_drop, seed, p_fwd, dp, absmax, dA, db2, st);
+    if (rc != SGS_OK) return rc;
+  } else {
     auto kern = edge_score_bwd_da_kernel<T, BN, H>;
     constexpr size_t used = (size_t)2 * (H / 64) * BN * 128 + 3 * kb::STAGE_BYTES + BN * 8 + 16 * 8 + 16;
     const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(NB, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp,
-                                                          absmax, dA, dw2, db1, db2);
+    kern<<<grid_for(NB, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, p_drop, seed, p_fwd, dp,
+                                                          absmax, dA, db2);
     SGS_LAUNCH_CHECK();
   }
   {
@@ -799,16 +811,17 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     constexpr size_t used = (size_t)2 * 2 * H * 128 + 3 * kb::STAGE_BYTES + 16 * 8 + 16;
     const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(H / 128, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, dA, absmax, d_out);
+    kern<<<grid_for(H / 128, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, w2, dA, absmax, d_out);
     SGS_LAUNCH_CHECK();
   }
   {
     auto kern = edge_score_bwd_dw_kernel<T, BN, H>;
     constexpr size_t stage = (size_t)64 * 2 * H * 2 + 64 * BN * 2;
     constexpr int nstage = (2 * stage + 4096 <= 232448) ? 2 : 1;
-    const size_t smem = nstage * stage + 128 + 1024;
+    const size_t smem = nstage * stage + 128 + BN * 4 + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(NB, ceil_div(n, 64)), kb::BW_THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, dW1);
+    kern<<<grid_for(NB, ceil_div(n, 64)), kb::BW_THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, W1, b1, w2,
+                                                                      dW1, db1, dw2);
     SGS_LAUNCH_CHECK();
   }
   return SGS_OK;

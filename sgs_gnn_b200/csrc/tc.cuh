@@ -319,4 +319,11 @@ struct Cvt<__half> {
   }
 };
 
+// Power-of-two loss scale of the scorer backward: keeps the 16-bit gate gradients S * dz / (1 - p_drop) in range
+// (max |S * dp| in [512, 1024]); it is divided out again in the fp32 epilogues.
+__device__ __forceinline__ float grad_scale(float absmax) {
+  if (!(absmax > 0.f) || isinf(absmax)) return 1.0f;
+  return exp2f(floorf(log2f(1024.0f / absmax)));
+}
+
 }  // namespace sgs

@@ -73,32 +73,41 @@ def _l2rel(a, r):
 
 
 def _emulated_grads(prec, out, ei, W1, b1, w2, b2, gup, keep, p_drop):
-    """fp32 CPU autograd of the quantised computation the TC kernels perform."""
+    """CPU emulation (fp64 accumulation) of the quantised computation the TC backward kernels perform
+    (csrc/edge_score_bwd_tc.cu): operands are rounded to 16 bit exactly where the kernels round them --
+    the node-embedding table, the features [x*y | x-y], W1 (recompute), the gate gradient
+    G = S*dz/(1-p)*[pre>0]*keep and the BF operand diag(w2).W1 -- and dW1 / db1 / dw2 are derived from
+    P = G^T F and g = colsum(G) as the BW epilogue does."""
     dt = TORCH_T[prec]
-    ste = lambda t: t + (t.to(dt).float() - t).detach()
+    q = lambda t: t.float().to(dt).double()
+    h = W1.shape[0]
+    w2v = w2.reshape(-1).double()
     absmax = float(gup.abs().max())
     S = 2.0 ** np.floor(np.log2(1024.0 / absmax))
-
-    class RoundGrad(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, z):
-            return z.view_as(z)
-
-        @staticmethod
-        def backward(ctx, g):
-            return (g * S).to(dt).float() / S
-
-    leaves = [t.clone().requires_grad_(True) for t in (out, W1, b1, w2.reshape(1, -1), b2)]
-    o, w1_, b1_, w2_, b2_ = leaves
-    oq = ste(o)
+    scale = 1.0 / (1.0 - p_drop) if keep is not None else 1.0
+    oq = q(out)
     x, y = oq[ei[0]], oq[ei[1]]
-    feat = torch.cat([ste(x * y), ste(x - y)], 1)
-    z = RoundGrad.apply(feat @ ste(w1_).t())
-    hid = torch.relu(z + b1_)
+    F = torch.cat([q(x * y), q(x - y)], 1)
+    pre = F @ q(W1).t() + b1.double()
+    mask = (pre > 0).double()
     if keep is not None:
-        hid = hid * keep / (1 - p_drop)
-    p = torch.sigmoid(hid @ w2_.t() + b2_).squeeze(-1)
-    return torch.autograd.grad((p * gup).sum(), leaves)
+        mask = mask * keep.double()
+    hid = pre * mask * scale
+    p = torch.sigmoid(hid @ w2v + b2.double().reshape(()))
+    dz = gup.double() * p * (1 - p)
+    G = q((S * dz * scale).float()[:, None] * mask.float())
+    dF = (G @ q(w2v.float()[:, None] * W1)) / S
+    dF1, dF2 = dF[:, :h], dF[:, h:]
+    d_out = torch.zeros_like(oq)
+    d_out.index_add_(0, ei[0], dF1 * y + dF2)
+    d_out.index_add_(0, ei[1], dF1 * x - dF2)
+    P = G.t() @ F / S
+    g = G.sum(0) / S
+    dW1 = w2v[:, None] * P
+    db1 = w2v * g
+    dw2 = ((W1.double() * P).sum(1) + b1.double() * g).reshape(1, -1)
+    db2 = dz.sum().reshape(1)
+    return d_out, dW1, db1, dw2, db2
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
