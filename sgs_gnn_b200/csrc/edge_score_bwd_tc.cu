@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include "scorer_producer.cuh"
+#include "tma.cuh"
 
 #include <type_traits>
 
@@ -289,23 +290,62 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 }
 
 // =============================================================================================
-// BF: dF = G . (diag(w2) W1)[:, column block]  and the scatter into d_out
+// BF: dF^T = (diag(w2) W1)[:, column block]^T . G^T   and the scatter into d_out
 // =============================================================================================
+// The product is computed TRANSPOSED: M = 128 node-embedding columns (TMEM lanes), N = 128 edges (TMEM columns).
+// An epilogue thread therefore owns ONE embedding column and walks the tile's edges along its registers:
+//   * the source-side sum over a run of equal sources (edge ids ascend by source) is a sequential in-register
+//     accumulation -- no shuffles, no cross-lane reduction; one RED per run and warp,
+//   * every RED (source and destination side) is a warp-coalesced 128-byte row segment: 32 lanes = 32 consecutive
+//     columns of one d_out row, i.e. whole 32-byte sectors at the L2 atomic units,
+//   * the gathers of x = tab[src], y = tab[dst] are 64-byte warp-coalesced 16-bit loads (the source row hits L1).
+// A = this kind's columns of diag(w2) W1, resident in smem ([H x 64] blocks, MN-major through the descriptor);
+// B = the G tile [128 e x 128 j] streamed by TMA (SWIZZLE_128B boxes) through a 3-stage ring -- no loader warps.
+// Roles: warp 0 TMA producer, warp 1 MMA issue + TMEM allocation, warps 2-17 epilogue: 4 groups of 4 warps (one
+// warp per TMEM lane quarter); group g drains accumulator buffer g & 1 (every other tile of this CTA), edges
+// [64 (g >> 1), +64) of the tile.
+namespace kbf {
+constexpr int TILE_E = 128;                    // edges per tile (N of the MMA)
+constexpr int CB = 128;                        // node-embedding columns per CTA kind (M of the MMA)
+constexpr int STAGE_BYTES = TILE_E * 128 * 2;  // [128 e x 128 j] 16-bit = two [128 x 64] boxes
+constexpr int NSTAGE = 3;
+constexpr int EPI_WARP0 = 2;
+constexpr int EPI_GROUPS = 4;
+constexpr int THREADS = (EPI_WARP0 + 4 * EPI_GROUPS) * 32;   // 576
+constexpr int CHUNK = 8;                       // edges per epilogue chunk
+}  // namespace kbf
+
+template <typename T>
+__device__ __forceinline__ float tab_to_float(unsigned short u);
+template <>
+__device__ __forceinline__ float tab_to_float<__half>(unsigned short u) { return __half2float(__ushort_as_half(u)); }
+template <>
+__device__ __forceinline__ float tab_to_float<__nv_bfloat16>(unsigned short u) {
+  return __uint_as_float((uint32_t)u << 16);
+}
+
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 template <typename T, int H>
-__global__ void __launch_bounds__(kb::THREADS, 1)
-edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+__global__ void __launch_bounds__(kbf::THREADS, 1)
+edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __restrict__ tab,
+                         const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
-                         const float* __restrict__ w2, const T* __restrict__ dA, const float* __restrict__ dp_absmax,
+                         const float* __restrict__ w2, const float* __restrict__ dp_absmax,
                          float* __restrict__ d_out) {
-  using namespace kb;
+  using namespace kbf;
   using namespace tc;
-  constexpr int CB = 128;                       // node-embedding columns per CTA kind
   constexpr int NKIND = H / CB;
-  constexpr int NQ = CB / 64;                   // 64-column groups (each: product block + difference block)
-  constexpr int BLK = H * 128;                  // one [H rows (j) x 64 k] 16-bit block
-  constexpr int B_BYTES = 2 * NQ * BLK;
-  constexpr int NJ = H / 128;                   // dA sub-tiles (128 hidden units each) per edge tile
-  constexpr int NSTAGE = 3;
+  constexpr int NQ = CB / 64;                   // 64-column blocks per part (product / difference)
+  constexpr int BLK = H * 128;                  // one [H rows (j) x 64 columns] 16-bit block
+  constexpr int A_BYTES = 2 * NQ * BLK;         // resident operand
+  constexpr int NJ = H / 128;                   // G sub-tiles (128 hidden units each) per edge tile
   static_assert(H % 128 == 0 && H <= 256, "unsupported shape");
 
   extern __shared__ uint8_t smem_raw[];
@@ -313,15 +353,15 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* sm = smem_raw + pad;
   const uint32_t sm_addr = raw_addr + pad;
-  constexpr uint32_t kUsed = B_BYTES + NSTAGE * STAGE_BYTES + 16 * 8 + 16;
+  constexpr uint32_t kUsed = A_BYTES + NSTAGE * STAGE_BYTES + 16 * 8 + 16;
   {
     uint32_t dyn_size;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
     if (pad + kUsed > dyn_size) __trap();
   }
-  const uint32_t b_base = sm_addr;
-  const uint32_t a_base = b_base + B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + B_BYTES + NSTAGE * STAGE_BYTES);
+  const uint32_t a_base = sm_addr;               // resident diag(w2) W1 blocks
+  const uint32_t g_base = a_base + A_BYTES;      // G stage ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + A_BYTES + NSTAGE * STAGE_BYTES);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t full0 = bar0, empty0 = bar0 + 32, dffull0 = bar0 + 64, dfempty0 = bar0 + 80;
@@ -329,38 +369,33 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kind = blockIdx.x % NKIND;
-  const int64_t ntiles = (n + TILE_M - 1) / TILE_M;
+  const int64_t ntiles = (n + TILE_E - 1) / TILE_E;
   const int64_t tile0 = blockIdx.x / NKIND;
   const int64_t tstep = gridDim.x / NKIND;
-  // Roles: the epilogue (gathers, TMEM reads, segment reduction, REDs) is the long pole of this kernel and the dA
-  // loaders are plain streaming loads, so 8 of the 13 warps drain accumulators: group 0 (warps 0-3) takes this
-  // CTA's even tiles / accumulator 0, group 1 (warps 9-12) the odd ones; warps 5-8 load dA, warp 4 issues MMAs.
-  constexpr int BF_PROD_WARP0 = MMA_WARP + 1, BF_PROD_WARPS = 4, BF_PROD_THREADS = BF_PROD_WARPS * 32;
-  constexpr int BF_EPI1_WARP0 = BF_PROD_WARP0 + BF_PROD_WARPS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(full0 + 8 * s, BF_PROD_THREADS);
+      mbar_init(full0 + 8 * s, 1);       // the producer's arrive.expect_tx; TMA completes the bytes
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(dffull0 + 8 * s, 1);
-      mbar_init(dfempty0 + 8 * s, EPI_THREADS);
+      mbar_init(dfempty0 + 8 * s, (EPI_GROUPS / 2) * 4 * 32);
     }
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) {
+  if (warp == 1) {
     tmem_alloc(smem_u32(tmem_ptr_s), 512);
     tmem_relinquish();
   }
   // resident operand: rows j = 0..H-1 of diag(w2) . W1, this kind's columns, as blocks [H x 64]:
-  //   block 2*qd   : product-part columns    kind*CB + 64*qd + [0,64)
-  //   block 2*qd+1 : difference-part columns H + kind*CB + 64*qd + [0,64)
+  //   block qd      : product-part columns    kind*CB + 64*qd + [0,64)
+  //   block NQ + qd : difference-part columns H + kind*CB + 64*qd + [0,64)
   for (int idx = threadIdx.x; idx < H * (2 * CB / 8); idx += THREADS) {
     const int j = idx / (2 * CB / 8);
     const int kc = idx % (2 * CB / 8);          // 16-byte chunk among this kind's 2*CB columns
-    const int blk = kc >> 3;                    // 0 .. 2*NQ-1 in (qd, half) order: blk = 2*qd + half
-    const int qd = blk >> 1, half = blk & 1;
+    const int blk = kc >> 3;                    // 0 .. 2*NQ-1: blk = half * NQ + qd
+    const int half = blk / NQ, qd = blk % NQ;
     const int c16 = kc & 7;
     const int kcol = (half ? H : 0) + kind * CB + qd * 64 + c16 * 8;
     const float* g = W1 + (int64_t)j * (2 * H) + kcol;
@@ -379,36 +414,28 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  const float invS = 1.0f / grad_scale(dp_absmax[0]);
 
-  if (warp >= BF_PROD_WARP0 && warp < BF_EPI1_WARP0) {
-    // ------------------------------- dA loaders: [128 e x 128 j] sub-tiles -------------------------------
-    const int pt = threadIdx.x - BF_PROD_WARP0 * 32;
-    const int c = pt & 15;          // 16-byte chunk (8 hidden units) inside the 128-unit sub-tile
-    const int row_base = pt >> 4;   // rows row_base + 8*i
-    uint32_t it = 0;
-    for (int64_t t = tile0; t < ntiles; t += tstep) {
+  if (warp == 0) {
+    // ------------------------------- TMA producer: G sub-tiles [128 e x 128 j] -------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = tile0; t < ntiles; t += tstep) {
 #pragma unroll 1
-      for (int js = 0; js < NJ; ++js, ++it) {
-        uint4 v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int64_t row = t * TILE_M + row_base + 8 * i;
-          v[i] = make_uint4(0, 0, 0, 0);
-          if (row < n) v[i] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + row * H + js * 128 + c * 8));
+        for (int js = 0; js < NJ; ++js, ++it) {
+          const uint32_t slot = it % NSTAGE;
+          mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(full0 + 8 * slot, STAGE_BYTES);
+          const uint32_t dst_s = g_base + slot * STAGE_BYTES;
+          // rows past n are zero-filled by TMA: dead edges contribute exact zeros
+          tma_load_2d(dst_s, &map_g, full0 + 8 * slot, js * 128, (int)(t * TILE_E));
+          tma_load_2d(dst_s + TILE_E * 128, &map_g, full0 + 8 * slot, js * 128 + 64, (int)(t * TILE_E));
         }
-        const uint32_t slot = it % NSTAGE;
-        mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
-        uint8_t* stage = sm + B_BYTES + slot * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          *reinterpret_cast<uint4*>(stage + (c >> 3) * (TILE_M * 128) + sw128_offset(row_base + 8 * i, c & 7)) = v[i];
-        mbar_arrive(full0 + 8 * slot);   // the MMA thread issues the proxy fence (see scorer_producer.cuh)
       }
     }
-  } else if (warp == MMA_WARP) {
+    __syncwarp();
+  } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, TILE_M, 128) | (1u << 16);  // B is MN-major
+      const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, CB, TILE_E) | (1u << 15);  // A is MN-major
       uint32_t it = 0, lt = 0;
       for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
         const uint32_t tb = lt & 1;
@@ -418,16 +445,15 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         for (int js = 0; js < NJ; ++js, ++it) {
           const uint32_t slot = it % NSTAGE;
           mbar_wait(full0 + 8 * slot, (it / NSTAGE) & 1);
-          fence_proxy_async_smem();   // loaders' generic-proxy stores -> async proxy
           tc_fence_after();
 #pragma unroll
-          for (int qd = 0; qd < NQ; ++qd) {
+          for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-              const uint64_t ad =
-                  umma_desc_k_sw128(a_base + slot * STAGE_BYTES + (kk >> 2) * (TILE_M * 128) + (kk & 3) * 32);
-              const uint64_t bd = umma_desc_mn_sw128(b_base + (2 * qd) * BLK + (js * 8 + kk) * 2048, BLK);
-              umma_f16(tmem_base + tb * 256 + qd * 128, ad, bd, idesc, (js | kk) != 0 ? 1u : 0u);
+              const uint64_t ad = umma_desc_mn_sw128(a_base + (half * NQ) * BLK + (js * 8 + kk) * 2048, BLK);
+              const uint64_t bd =
+                  umma_desc_k_sw128(g_base + slot * STAGE_BYTES + (kk >> 2) * (TILE_E * 128) + (kk & 3) * 32);
+              umma_f16(tmem_base + tb * 256 + half * 128, ad, bd, idesc, (js | kk) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty0 + 8 * slot);
@@ -437,103 +463,91 @@ edge_score_bwd_df_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     }
     __syncwarp();
   } else {
-    // ------------------------------- epilogue: dF -> d_out[src], d_out[dst] -------------------------------
-    const int lg = warp & 3;
-    const int r = lg * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
-    const uint32_t grp = warp >= BF_EPI1_WARP0 ? 1u : 0u;
-    for (int64_t t = tile0 + grp * tstep, lt = grp; t < ntiles; t += 2 * tstep, lt += 2) {
-      const uint32_t tb = grp;   // == lt & 1
-      const int64_t i = t * TILE_M + r;
-      const bool live = i < n;
-      int64_t e = live ? i : n - 1;
-      if (ids) e = ids[e];
-      const int s_node = src[e], d_node = dst[e];
-      const T* xrow = tab + (int64_t)s_node * H;
-      const T* yrow = tab + (int64_t)d_node * H;
-      float* dyrow = d_out + (int64_t)d_node * H;
-      // the embedding-row slices of slice `part + 1` are in flight while slice `part` is reduced; the first ones
-      // are issued before the accumulator is waited for
-      uint4 nx0, nx1, ny0, ny1;
-      {
-        const int c0 = kind * CB;
-        nx0 = *reinterpret_cast<const uint4*>(xrow + c0);
-        nx1 = *reinterpret_cast<const uint4*>(xrow + c0 + 8);
-        ny0 = *reinterpret_cast<const uint4*>(yrow + c0);
-        ny1 = *reinterpret_cast<const uint4*>(yrow + c0 + 8);
+    // ------------------------------- epilogue: dF^T -> d_out[src], d_out[dst] -------------------------------
+    const int lg = warp & 3;                        // TMEM lane quarter this warp may read
+    const int grp = (warp - EPI_WARP0) >> 2;
+    const uint32_t tb = grp & 1;
+    const int eh = grp >> 1;                        // which 64 edges of the tile
+    const int c = kind * CB + lg * 32 + lane;       // this thread's node-embedding column
+    const unsigned short* tabc = reinterpret_cast<const unsigned short*>(tab) + c;
+    float* doc = d_out + c;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + tb * 256 + eh * 64;
+    const float invS = 1.0f / grad_scale(dp_absmax[0]);
+    constexpr int EPL = 64 / 32;                    // edges per lane and tile half
+    int sn[EPL], dn[EPL], sn2[EPL], dn2[EPL];
+    auto load_endpoints = [&](int64_t t, int* s, int* d) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int64_t i = t * TILE_E + eh * 64 + 32 * k + lane;
+        s[k] = -1;
+        d[k] = 0;
+        if (i < n) {
+          const int64_t e = ids ? ids[i] : i;
+          s[k] = src[e];
+          d[k] = dst[e];
+        }
       }
+    };
+    int64_t t = tile0 + tb * tstep;
+    uint32_t lt = tb;
+    if (t < ntiles) load_endpoints(t, sn, dn);
+    for (; t < ntiles; t += 2 * tstep, lt += 2) {
+      // the endpoints of this group's next tile are in flight while this one is reduced
+      if (t + 2 * tstep < ntiles) load_endpoints(t + 2 * tstep, sn2, dn2);
       mbar_wait(dffull0 + 8 * tb, (lt >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int part = 0; part < NQ * 4; ++part) {
-        const int qd = part >> 2, q16 = part & 3;                     // 16-column slice q16 of column group qd
-        const int col0 = kind * CB + qd * 64 + q16 * 16;              // 16 node-embedding columns
-        const uint4 xv0 = nx0, xv1 = nx1, yv0 = ny0, yv1 = ny1;
-        if (part + 1 < NQ * 4) {
-          const int cn = kind * CB + ((part + 1) >> 2) * 64 + ((part + 1) & 3) * 16;
-          nx0 = *reinterpret_cast<const uint4*>(xrow + cn);
-          nx1 = *reinterpret_cast<const uint4*>(xrow + cn + 8);
-          ny0 = *reinterpret_cast<const uint4*>(yrow + cn);
-          ny1 = *reinterpret_cast<const uint4*>(yrow + cn + 8);
+      int cur_s = __shfl_sync(0xffffffffu, sn[0], 0);
+      float acc = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 64 / CHUNK; ++ch) {
+        constexpr int CPL = 32 / CHUNK;             // chunks per endpoint register
+        const int k = ch / CPL, bl = (ch % CPL) * CHUNK;
+        uint32_t f1[CHUNK], f2[CHUNK];
+        tmem_ld8(taddr0 + ch * CHUNK, f1);
+        tmem_ld8(taddr0 + 128 + ch * CHUNK, f2);
+        int s[CHUNK], d[CHUNK];
+        unsigned short xv[CHUNK], yv[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          s[j] = __shfl_sync(0xffffffffu, sn[k], bl + j);
+          d[j] = __shfl_sync(0xffffffffu, dn[k], bl + j);
         }
-        uint32_t f1[16], f2[16];
-        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + q16 * 16, f1);
-        tmem_ld16(tmem_base + lane_off + tb * 256 + qd * 128 + 64 + q16 * 16, f2);
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          xv[j] = __ldg(tabc + (int64_t)(s[j] < 0 ? 0 : s[j]) * H);
+          yv[j] = __ldg(tabc + (int64_t)d[j] * H);
+        }
         tmem_ld_wait();
-        if (part == NQ * 4 - 1) {  // all of this tile's accumulator has been read
+        if (ch == 64 / CHUNK - 1) {  // this warp has read all of its part of the accumulator
           tc_fence_before();
           mbar_arrive(dfempty0 + 8 * tb);
         }
-        const uint32_t xs[8] = {xv0.x, xv0.y, xv0.z, xv0.w, xv1.x, xv1.y, xv1.z, xv1.w};
-        const uint32_t ys[8] = {yv0.x, yv0.y, yv0.z, yv0.w, yv1.x, yv1.y, yv1.z, yv1.w};
-        float gx[16], gy[16];
-        const float sc = live ? invS : 0.f;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const float2 xa = Cvt<T>::unpack(xs[m]);
-          const float2 ya = Cvt<T>::unpack(ys[m]);
-          const float a0 = __uint_as_float(f1[2 * m]) * sc, a1 = __uint_as_float(f1[2 * m + 1]) * sc;
-          const float d0 = __uint_as_float(f2[2 * m]) * sc, d1 = __uint_as_float(f2[2 * m + 1]) * sc;
-          gx[2 * m] = fmaf(a0, ya.x, d0);
-          gx[2 * m + 1] = fmaf(a1, ya.y, d1);
-          gy[2 * m] = fmaf(a0, xa.x, -d0);
-          gy[2 * m + 1] = fmaf(a1, xa.y, -d1);
+        for (int j = 0; j < CHUNK; ++j) {
+          if (s[j] != cur_s) {          // warp-uniform: a new run of equal sources starts
+            if (cur_s >= 0) atomicAdd(doc + (int64_t)cur_s * H, acc);
+            acc = 0.f;
+            cur_s = s[j];
+          }
+          if (s[j] >= 0) {              // live edge (warp-uniform)
+            const float a = __uint_as_float(f1[j]) * invS, b = __uint_as_float(f2[j]) * invS;
+            acc += fmaf(a, tab_to_float<T>(yv[j]), b);
+            atomicAdd(doc + (int64_t)d[j] * H, fmaf(a, tab_to_float<T>(xv[j]), -b));
+          }
         }
-        // destination side: random rows -> 128-bit vector RED per row
-        if (live) {
+      }
+      if (cur_s >= 0) atomicAdd(doc + (int64_t)cur_s * H, acc);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            red_add_v4(dyrow + col0 + 4 * k, gy[4 * k], gy[4 * k + 1], gy[4 * k + 2], gy[4 * k + 3]);
-        }
-        // source side: rows of a warp mostly share their source (edge ids ascend by source): reduce each run
-        // of equal sources across the warp first, then one coalesced RED from 16 lanes.
-        uint32_t todo = __ballot_sync(0xffffffffu, live);
-#pragma unroll 1
-        for (int iter = 0; iter < 2 && todo; ++iter) {
-          const int leader = __ffs(todo) - 1;
-          const int s_lead = __shfl_sync(0xffffffffu, s_node, leader);
-          const bool in_seg = live && s_node == s_lead && ((todo >> lane) & 1u);
-          const uint32_t seg = __ballot_sync(0xffffffffu, in_seg);
-          float v[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = in_seg ? gx[k] : 0.f;
-          const float tot = warp_colsum16(v, lane);
-          if (lane < 16) atomicAdd(d_out + (int64_t)s_lead * H + col0 + lane, tot);
-          todo &= ~seg;
-        }
-        if ((todo >> lane) & 1u) {
-          float* dxrow = d_out + (int64_t)s_node * H;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            red_add_v4(dxrow + col0 + 4 * k, gx[4 * k], gx[4 * k + 1], gx[4 * k + 2], gx[4 * k + 3]);
-        }
+      for (int k = 0; k < EPL; ++k) {
+        sn[k] = sn2[k];
+        dn[k] = dn2[k];
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -808,10 +822,15 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
   }
   {
     auto kern = edge_score_bwd_df_kernel<T, H>;
-    constexpr size_t used = (size_t)2 * 2 * H * 128 + 3 * kb::STAGE_BYTES + 16 * 8 + 16;
+    CUtensorMap map_g;
+    if (!make_map_16bit(&map_g, dA, n, H, H, kbf::TILE_E, std::is_same<T, __nv_bfloat16>::value)) {
+      set_error("sgs_edge_score_bwd: cuTensorMapEncodeTiled failed");
+      return SGS_E_CUDA;
+    }
+    constexpr size_t used = (size_t)2 * 2 * H * 128 + kbf::NSTAGE * kbf::STAGE_BYTES + 16 * 8 + 16;
     const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(H / 128, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, w2, dA, absmax, d_out);
+    kern<<<grid_for(H / 128, ntiles), kbf::THREADS, smem, st>>>(map_g, tab, src, dst, ids, n, W1, w2, absmax, d_out);
     SGS_LAUNCH_CHECK();
   }
   {

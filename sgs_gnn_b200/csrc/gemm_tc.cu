@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "tma.cuh"
 
 namespace sgs {
 
@@ -26,22 +27,6 @@ constexpr int STAGE_BYTES = (BM + BN) * BK * 4;     // 32 KB
 constexpr int NSTAGE = 6;
 constexpr int THREADS = 6 * 32;
 }  // namespace k4
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 
 // 2-D fp32 tensor [rows, inner] with row stride ld (elements); box = [box_rows x 32 floats], 128-byte swizzle
 static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t K, int64_t ld,
@@ -55,13 +40,6 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t K,
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
 }
 
 template <bool TN>
