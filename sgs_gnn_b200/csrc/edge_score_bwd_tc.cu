@@ -26,6 +26,7 @@
 #include "scorer_producer.cuh"
 #include "tma.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <type_traits>
 
 namespace sgs {
@@ -33,7 +34,7 @@ namespace sgs {
 int32_t edge_score_bwd_gate_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
                                  const int32_t* ids, int64_t n, const float* W1, const float* b1, float p_drop,
                                  uint64_t seed, const float* p_fwd, const float* dp, const float* dp_absmax,
-                                 void* g_out, float* db2, cudaStream_t st);
+                                 void* g_out, float* db2, const int32_t* key_ids, cudaStream_t st);
 
 
 namespace kb {
@@ -101,7 +102,8 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
                          const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
                          const float* __restrict__ b1, float p_drop, uint64_t seed,
                          const float* __restrict__ p_fwd, const float* __restrict__ dp,
-                         const float* __restrict__ dp_absmax, T* __restrict__ g_out, float* __restrict__ db2) {
+                         const float* __restrict__ dp_absmax, T* __restrict__ g_out, float* __restrict__ db2,
+                         const int32_t* __restrict__ key_ids) {
   using namespace kb;
   using namespace tc;
   constexpr int NB = H / BN;
@@ -229,9 +231,12 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
       float dz = 0.f;
       uint32_t rowkey = 0;
       if (live) {
-        const float pe = p_fwd[i];
-        dz = dp[i] * pe * (1.0f - pe);
-        if (drop) rowkey = dropout_rowkey(seed, (uint64_t)(ids ? ids[i] : i));
+        dz = dp[i];   // p_fwd == nullptr: dp already holds dz = dp * p * (1 - p)
+        if (p_fwd) {
+          const float pe = p_fwd[i];
+          dz *= pe * (1.0f - pe);
+        }
+        if (drop) rowkey = dropout_rowkey(seed, (uint64_t)(key_ids ? key_ids[i] : (ids ? ids[i] : i)));
       }
       acc_b2 += dz;
       const float g = dz * gscale;
@@ -770,10 +775,62 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 }
 
 // =============================================================================================
+// Pre-pass: destination-range bucketing of the edge list
+// =============================================================================================
+// The backward touches, per edge, the rows tab[dst] (gather) and d_out[dst] (RED) of a random destination: with
+// N x H x 6 bytes of such rows (358 MB at Reddit scale) against 126 MB of L2, ~3/4 of the RED sectors and most
+// gathers missed (ncu r01g: BF 46 GB of DRAM traffic for 12 GB of useful G reads).  The edges are therefore
+// processed grouped by destination RANGE (2^r rows whose tab + d_out rows fit in L2), stably -- inside a bucket
+// edge ids still ascend by source, so the source-side run sums keep working (runs get shorter).  All three
+// kernels just see a permuted id list ids_b plus dz in the same order; every output is an order-independent sum.
+__global__ void bucket_key_kernel(const int32_t* __restrict__ dst, const int32_t* __restrict__ ids, int64_t n,
+                                  int shift, uint8_t* __restrict__ key, int32_t* __restrict__ pos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int64_t e = ids ? ids[i] : i;
+    key[i] = (uint8_t)(dst[e] >> shift);
+    pos[i] = (int32_t)i;
+  }
+}
+// in bucket order: ids_b[i'] = edge id (dropout mask key), its endpoints src_b / dst_b (so that no kernel chases
+// ids -> src/dst on its critical path) and dz_b[i'] = dp * p * (1 - p)
+__global__ void bucket_gather_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ ids,
+                                     const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                     const float* __restrict__ p_fwd, const float* __restrict__ dp, int64_t n,
+                                     int32_t* __restrict__ ids_b, int32_t* __restrict__ src_b,
+                                     int32_t* __restrict__ dst_b, float* __restrict__ dz_b) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int64_t o = pos ? pos[i] : i;
+    const int64_t e = ids ? ids[o] : o;
+    ids_b[i] = (int32_t)e;
+    src_b[i] = src[e];
+    dst_b[i] = dst[e];
+    const float pe = p_fwd[o];
+    dz_b[i] = dp[o] * pe * (1.0f - pe);
+  }
+}
+
+static size_t bucket_temp_bound(int64_t n) { return (size_t)(32u << 20) + (size_t)(n / 8) * 4; }
+// rows per bucket = 2^shift: tab (2 B) + d_out (4 B) rows of one bucket within ~64 MB; at most 256 buckets
+static int bucket_shift(int64_t N, int64_t H) {
+  int shift = 0;
+  while (((int64_t)2 << shift) * H * 6 <= ((int64_t)64 << 20)) ++shift;
+  while (((N - 1) >> shift) > 255) ++shift;
+  return shift;
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t edge_score_bwd_tc_workspace_bytes(int64_t n, int64_t N, int64_t H) {
-  return 2048 + (size_t)N * H * 2 + (size_t)n * H * 2;
+  // absmax | tab [N,H] 16 bit | G [n,H] 16 bit | ids_b, src_b, dst_b, dz_b, pos_a, pos_b [n] 32 bit |
+  // key_a, key_b [n] 8 bit | cub temp
+  return 4096 + align256((size_t)N * H * 2) + align256((size_t)n * H * 2) + 6 * align256((size_t)n * 4) +
+         2 * align256((size_t)n) + bucket_temp_bound(n);
 }
 
 template <typename T, int H>
@@ -788,9 +845,21 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     return SGS_E_WORKSPACE;
   }
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  float* absmax = reinterpret_cast<float*>(base);
-  T* tab = reinterpret_cast<T*>(base + 256);
-  T* dA = reinterpret_cast<T*>(base + 256 + (((size_t)N * H * 2 + 255) & ~(size_t)255));
+  uint8_t* cur = base;
+  auto take = [&](size_t bytes) { uint8_t* p = cur; cur += align256(bytes); return p; };
+  float* absmax = reinterpret_cast<float*>(take(256));
+  T* tab = reinterpret_cast<T*>(take((size_t)N * H * 2));
+  T* dA = reinterpret_cast<T*>(take((size_t)n * H * 2));
+  int32_t* ids_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
+  int32_t* src_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
+  int32_t* dst_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
+  float* dz_b = reinterpret_cast<float*>(take((size_t)n * 4));
+  int32_t* pos_a = reinterpret_cast<int32_t*>(take((size_t)n * 4));
+  int32_t* pos_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
+  uint8_t* key_a = take((size_t)n);
+  uint8_t* key_b = take((size_t)n);
+  void* cub_temp = cur;
+  const size_t cub_avail = ws_bytes - (size_t)(cur - reinterpret_cast<uint8_t*>(ws));
   SGS_CUDA(cudaMemsetAsync(absmax, 0, 4, st));
   const int64_t cap = (int64_t)sm_count() * 16;
   int64_t g = ceil_div(n, 256);
@@ -800,6 +869,39 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
   g = ceil_div(n8, 256);
   convert_rows_kernel_b<T><<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(out, n8, reinterpret_cast<uint4*>(tab));
   SGS_LAUNCH_CHECK();
+  // ---- destination-range bucketing: ids_b (bucket order, stable), dz_b ----
+  {
+    const int shift = bucket_shift(N, H);
+    const int nbuckets = (int)(((N - 1) >> shift) + 1);
+    const int32_t* pos = nullptr;
+    g = ceil_div(n, 256);
+    const unsigned eg = (unsigned)(g > cap ? cap : g);
+    if (nbuckets > 1) {
+      int bits = 1;
+      while ((1 << bits) < nbuckets) ++bits;
+      bucket_key_kernel<<<eg, 256, 0, st>>>(dst, ids, n, shift, key_a, pos_a);
+      SGS_LAUNCH_CHECK();
+      cub::DoubleBuffer<uint8_t> dk(key_a, key_b);
+      cub::DoubleBuffer<int32_t> dv(pos_a, pos_b);
+      size_t need = 0;
+      SGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)n, 0, bits, st));
+      if (need > cub_avail) {
+        set_error("sgs_edge_score_bwd: cub temp %zu > available %zu", need, cub_avail);
+        return SGS_E_WORKSPACE;
+      }
+      SGS_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, need, dk, dv, (int)n, 0, bits, st));
+      count_launch(2);
+      pos = dv.Current();
+    }
+    bucket_gather_kernel<<<eg, 256, 0, st>>>(pos, ids, src, dst, p_fwd, dp, n, ids_b, src_b, dst_b, dz_b);
+    SGS_LAUNCH_CHECK();
+    // from here on the edge list is (src_b, dst_b) in bucket order, addressed directly
+    src = src_b;
+    dst = dst_b;
+    ids = nullptr;
+    dp = dz_b;
+    p_fwd = nullptr;  // dp holds dz
+  }
   const int64_t ntiles = ceil_div(n, kb::TILE_M);
   auto grid_for = [&](int kinds, int64_t items) {
     int64_t gr = (int64_t)(sm_count() / kinds) * kinds;
@@ -809,7 +911,7 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
   if (H == 256 && n >= 2 * kb::TILE_M) {
     // CTA pairs: every edge tile is gathered and built once (edge_score_tc2.cu, MODE 1)
     const int32_t rc = edge_score_bwd_gate_pair(tab, std::is_same<T, __nv_bfloat16>::value ? 1 : 0, src, dst, ids, n,
-                                                W1, b1, p_drop, seed, p_fwd, dp, absmax, dA, db2, st);
+                                                W1, b1, p_drop, seed, p_fwd, dp, absmax, dA, db2, ids_b, st);
     if (rc != SGS_OK) return rc;
   } else {
     auto kern = edge_score_bwd_da_kernel<T, BN, H>;
@@ -817,7 +919,7 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_for(NB, ntiles), kb::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, p_drop, seed, p_fwd, dp,
-                                                          absmax, dA, db2);
+                                                          absmax, dA, db2, ids_b);
     SGS_LAUNCH_CHECK();
   }
   {

@@ -65,7 +65,7 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                       float p_drop, uint64_t seed, float* __restrict__ p_out, const float* __restrict__ p_fwd,
                       const float* __restrict__ dp, const float* __restrict__ dp_absmax, T* __restrict__ g_out,
-                      float* __restrict__ db2) {
+                      float* __restrict__ db2, const int32_t* __restrict__ key_ids) {
   using namespace k1p;
   using namespace tc;
 
@@ -225,15 +225,19 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
       uint32_t rowkey = 0;
       if (drop) {
         int64_t e = i < n ? i : n - 1;
-        if (ids) e = ids[e];
+        if (key_ids) e = key_ids[e];   // the edge list was re-ordered by the caller: original ids for the mask
+        else if (ids) e = ids[e];
         rowkey = dropout_rowkey(seed, (uint64_t)e);
       }
       uint32_t g_lo = 0, g_hi = 0;   // MODE 1: this row's gate gradient in the low / high 16 bits
       if (MODE == 1) {
         float dz = 0.f;
         if (i < n) {
-          const float pe = p_fwd[i];
-          dz = dp[i] * pe * (1.0f - pe);
+          dz = dp[i];   // p_fwd == nullptr: the caller passes dz = dp * p * (1 - p) itself
+          if (p_fwd) {
+            const float pe = p_fwd[i];
+            dz *= pe * (1.0f - pe);
+          }
         }
         acc_b2 += dz;
         const float g = dz * gscale;
@@ -330,7 +334,7 @@ static int32_t launch_k1_pair(const T* tab, const int32_t* src, const int32_t* d
                               const float* W1, const float* b1, const float* w2, const float* b2, float p_drop,
                               uint64_t seed, float* p, cudaStream_t st, const float* p_fwd = nullptr,
                               const float* dp = nullptr, const float* dp_absmax = nullptr, T* g_out = nullptr,
-                              float* db2 = nullptr) {
+                              float* db2 = nullptr, const int32_t* key_ids = nullptr) {
   size_t smem = (size_t)k1p::USED_BYTES + 1024;
   if (smem > 232448) smem = 232448;
   auto kern = edge_score_tc2_kernel<T, MODE>;
@@ -339,7 +343,7 @@ static int32_t launch_k1_pair(const T* tab, const int32_t* src, const int32_t* d
   int64_t pairs = sm_count() / 2;
   if (pairs > ndt) pairs = ndt;
   kern<<<(unsigned)(2 * pairs), k1p::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p,
-                                                          p_fwd, dp, dp_absmax, g_out, db2);
+                                                          p_fwd, dp, dp_absmax, g_out, db2, key_ids);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }
@@ -359,13 +363,13 @@ int32_t edge_score_fwd_pair(const void* tab, int32_t is_bf16, const int32_t* src
 int32_t edge_score_bwd_gate_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
                                  const int32_t* ids, int64_t n, const float* W1, const float* b1, float p_drop,
                                  uint64_t seed, const float* p_fwd, const float* dp, const float* dp_absmax,
-                                 void* g_out, float* db2, cudaStream_t st) {
+                                 void* g_out, float* db2, const int32_t* key_ids, cudaStream_t st) {
   if (is_bf16)
     return launch_k1_pair<__nv_bfloat16, 1>(reinterpret_cast<const __nv_bfloat16*>(tab), src, dst, ids, n, W1, b1, b1,
                                             b1, p_drop, seed, nullptr, st, p_fwd, dp, dp_absmax,
-                                            reinterpret_cast<__nv_bfloat16*>(g_out), db2);
+                                            reinterpret_cast<__nv_bfloat16*>(g_out), db2, key_ids);
   return launch_k1_pair<__half, 1>(reinterpret_cast<const __half*>(tab), src, dst, ids, n, W1, b1, b1, b1, p_drop,
-                                   seed, nullptr, st, p_fwd, dp, dp_absmax, reinterpret_cast<__half*>(g_out), db2);
+                                   seed, nullptr, st, p_fwd, dp, dp_absmax, reinterpret_cast<__half*>(g_out), db2, key_ids);
 }
 
 }  // namespace sgs
