@@ -400,7 +400,10 @@ def run_gpu_arm(a):
         "edge_grad_d256": ("hbm", nnz * (2 * 4 * 256 + 12)),
         f"edge_grad_d{c}": ("hbm", nnz * (2 * 4 * c + 12)),
         "sample_topq": ("hbm", e_k1 * 20 + q_loc * 12),
-        "loss_bwd": ("hbm", q_loc * (2 * 4 * c + 14 + 2 * 4 * c + 4) + n_train * (4 * c + 8)),
+        # K5: the fused forward sweep reads 2 logit rows + ids + p per sampled edge AND accumulates
+        # the unscaled row gradients (2 rows), writes u1/u2; the backward is the two streaming passes left over
+        "loss_fwd": ("hbm", q_loc * (2 * 4 * c + 12 + 2 * 4 * c + 8) + n * (4 * c + 9)),
+        "loss_bwd": ("hbm", q_loc * 12 + n * (3 * 4 * c + 9)),
     }
     kernels = []
     for name, (bound, work) in alg.items():

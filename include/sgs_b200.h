@@ -254,6 +254,26 @@ int32_t sgs_loss_bwd(const float* logits, int64_t N, int64_t C, const int64_t* y
                      float c1, float c2, int32_t reg1, int32_t reg2, const float* gscale,
                      float* dlogits, float* dp_s, sgs_stream_t stream);
 
+
+/* One-sweep variant of the two calls above for the learned step (training_hybrid.py:103-135): the forward pass
+ * over the sampled edges also leaves the UNSCALED gradients of the edge terms behind --
+ *   u_reg1[q] = (p - label) / max(p (1 - p), 1e-12) (0 outside the train mask), u_reg2[q] = p - cos,
+ *   dlog_e[N,C] = sum over incident sampled edges of (cos - p) * d cos / d logits   (zeroed here) --
+ * so that sgs_loss_bwd_fused is two streaming passes (dp_s = g1 u_reg1 + g2 u_reg2, dlogits = CE part + g2 dlog_e)
+ * with the scalars g1 = g c1 / n_valid [sum_label > 1], g2 = 2 g c2 / q read from acc on the device.
+ * node_code: int32 [N] scratch (train ? y : -1).  Needs C <= 64; the sampled edges must ascend by source (they do:
+ * ascending edge id of a (src,dst)-sorted edge list) for the source-side run accumulation to pay off -- any order
+ * is still correct. */
+int32_t sgs_loss_fwd_fused(const float* logits, int64_t N, int64_t C, const int64_t* y,
+                           const uint8_t* train_mask, const uint8_t* row_mask, const int32_t* s_src,
+                           const int32_t* s_dst, const float* p_s, int64_t q, double* acc, float* dlog_e,
+                           float* u_reg1, float* u_reg2, int32_t* node_code, sgs_stream_t stream);
+int32_t sgs_loss_bwd_fused(const float* logits, int64_t N, int64_t C, const int64_t* y,
+                           const uint8_t* train_mask, const uint8_t* row_mask, int64_t q, const double* acc,
+                           float c0, float c1, float c2, int32_t reg1, int32_t reg2, const float* gscale,
+                           const float* dlog_e, const float* u_reg1, const float* u_reg2, float* dlogits,
+                           float* dp_s, sgs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,8 @@ SIGNATURES = {
     "sgs_loss_fwd": (I32, [P, I64, I64, P, P, P, P, P, P, I64, I32, P, P]),
     "sgs_loss_finish": (I32, [P, F32, F32, F32, I32, I32, P, P]),
     "sgs_loss_bwd": (I32, [P, I64, I64, P, P, P, P, P, P, I64, I32, P, F32, F32, F32, I32, I32, P, P, P, P]),
+    "sgs_loss_fwd_fused": (I32, [P, I64, I64, P, P, P, P, P, P, I64, P, P, P, P, P, P]),
+    "sgs_loss_bwd_fused": (I32, [P, I64, I64, P, P, P, I64, P, F32, F32, F32, I32, I32, P, P, P, P, P, P, P]),
 }
 
 PREC_FP32, PREC_BF16, PREC_FP16, PREC_TF32 = 0, 1, 2, 3

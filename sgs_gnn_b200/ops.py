@@ -689,12 +689,44 @@ class LossStats:
     __slots__ = ("acc",)
 
 
+class EdgeLossState:
+    """What the fused edge pass (sgs_loss_fwd_fused) leaves behind for the backward: the unscaled gradients of the
+    reg1 / reg2 terms w.r.t. the sampled edge probabilities and the logits."""
+    __slots__ = ("dlog_e", "u1", "u2", "q")
+
+    def __init__(self, dlog_e, u1, u2, q):
+        self.dlog_e, self.u1, self.u2, self.q = dlog_e, u1, u2, q
+
+
+_FUSED_MAX_CLASSES = 64
+_edge_states = {}   # id(acc tensor) -> EdgeLossState of the forward that produced it (one live entry per step)
+
+
+def edge_state_of(acc):
+    st = _edge_states.get(id(acc))
+    return st[1] if st is not None and st[0]() is acc else None
+
+
 def loss_forward(logits, y, train_mask_u8, sub=None, p_s=None, row_mask_u8=None):
     logits = _req(logits, torch.float32, "logits")
     n, c = logits.shape
     acc = torch.empty(8, dtype=torch.float64, device=logits.device)
     with_edges = sub is not None
     q = sub.num_edges if with_edges else 0
+    if with_edges and q > 0 and c <= _FUSED_MAX_CLASSES:
+        # learned step: one sweep over the sampled edges computes the loss sums and the unscaled edge-term gradients
+        p_s = _req(p_s, torch.float32, "edge_probs")
+        dlog_e = torch.empty_like(logits)
+        u1, u2 = _vec(q, torch.float32, logits.device), _vec(q, torch.float32, logits.device)
+        code = torch.empty(n, dtype=torch.int32, device=logits.device)
+        with _timed("loss_fwd"):
+            check(lib().sgs_loss_fwd_fused(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(row_mask_u8), _p(sub.src),
+                                           _p(sub.dst), _p(p_s), q, _p(acc), _p(dlog_e), _p(u1), _p(u2), _p(code),
+                                           _stream()), "sgs_loss_fwd_fused")
+        import weakref
+        _edge_states.clear()
+        _edge_states[id(acc)] = (weakref.ref(acc), EdgeLossState(dlog_e, u1, u2, q))
+        return acc
     check(lib().sgs_loss_fwd(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(row_mask_u8),
                              _p(sub.src) if with_edges else None,
                              _p(sub.dst) if with_edges else None, _p(p_s) if with_edges else None, q,
@@ -707,7 +739,8 @@ class FusedLossFn(torch.autograd.Function):
     (training_hybrid.py:103-132).  `acc` may be a precomputed sgs_loss_fwd accumulator."""
 
     @staticmethod
-    def forward(ctx, logits, p_s, y, train_mask_u8, sub, c0, c1, c2, reg1, reg2, acc, row_mask_u8=None):
+    def forward(ctx, logits, p_s, y, train_mask_u8, sub, c0, c1, c2, reg1, reg2, acc, row_mask_u8=None,
+                edge_state=None):
         logits = _req(logits, torch.float32, "logits")
         with_edges = sub is not None and p_s is not None and (reg1 or reg2)
         if with_edges:
@@ -715,6 +748,9 @@ class FusedLossFn(torch.autograd.Function):
         if acc is None:
             acc = loss_forward(logits, y, train_mask_u8, sub if with_edges else None, p_s if with_edges else None,
                                row_mask_u8)
+        if edge_state is None and with_edges:
+            edge_state = edge_state_of(acc)
+        ctx.edge_state = edge_state if with_edges else None
         loss = torch.empty(1, dtype=torch.float32, device=logits.device)
         check(lib().sgs_loss_finish(_p(acc), c0, c1, c2, 1 if (reg1 and with_edges) else 0,
                                     1 if (reg2 and with_edges) else 0, _p(loss), _stream()), "sgs_loss_finish")
@@ -731,15 +767,24 @@ class FusedLossFn(torch.autograd.Function):
         dlogits = torch.empty_like(logits)
         dp = _vec(p_s.numel(), torch.float32, p_s.device) if ctx.with_edges else None
         q = sub.num_edges if ctx.with_edges else 0
+        est = ctx.edge_state
+        if est is not None:
+            with _timed("loss_bwd"):
+                check(lib().sgs_loss_bwd_fused(_p(logits), n, c, _p(y), _p(tm), _p(rm), est.q, _p(acc), ctx.c0, ctx.c1,
+                                               ctx.c2, 1 if ctx.reg1 else 0, 1 if ctx.reg2 else 0, _p(g),
+                                               _p(est.dlog_e), _p(est.u1), _p(est.u2), _p(dlogits), _p(dp),
+                                               _stream()), "sgs_loss_bwd_fused")
+            ctx.edge_state = None
+            return dlogits, dp, None, None, None, None, None, None, None, None, None, None, None
         with _timed("loss_bwd"):
           check(lib().sgs_loss_bwd(_p(logits), n, c, _p(y), _p(tm), _p(rm), _p(sub.src) if ctx.with_edges else None,
                                  _p(sub.dst) if ctx.with_edges else None, _p(p_s), q, 1 if ctx.with_edges else 0,
                                  _p(acc), ctx.c0, ctx.c1, ctx.c2, 1 if ctx.reg1 else 0, 1 if ctx.reg2 else 0, _p(g),
                                  _p(dlogits), _p(dp), _stream()), "sgs_loss_bwd")
-        return dlogits, dp, None, None, None, None, None, None, None, None, None, None
+        return dlogits, dp, None, None, None, None, None, None, None, None, None, None, None
 
 
 def fused_loss(logits, y, train_mask_u8, p_s=None, sub=None, c1=1.0, c2=0.5, reg1=True, reg2=True, acc=None,
-               c0=1.0, row_mask_u8=None):
+               c0=1.0, row_mask_u8=None, edge_state=None):
     return FusedLossFn.apply(logits, p_s, y, train_mask_u8, sub, float(c0), float(c1), float(c2), bool(reg1),
-                             bool(reg2), acc, row_mask_u8)
+                             bool(reg2), acc, row_mask_u8, edge_state)

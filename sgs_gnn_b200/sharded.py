@@ -472,6 +472,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
     with_edges = bool(args.reg1 or args.reg2)
     acc_l = ops.loss_forward(learned_out.detach(), sb.y, tm_full, lg_s.graph if with_edges else None,
                              p_s.detach() if with_edges else None, row_mask_u8=tm_owned)
+    est_l = ops.edge_state_of(acc_l)   # acc_l is re-sliced from the all-reduced sums below: keep its edge state
     acc_r = random_out = None
     if args.conditional:
         random_out = gnn_forward(model, sb.x, lg_rand)
@@ -489,7 +490,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
     if update_edge_mlp:
         loss = ops.fused_loss(learned_out, sb.y, tm_full, p_s if with_edges else None,
                               lg_s.graph if with_edges else None, args.regularizer1_coef, args.consist_reg_coef,
-                              bool(args.reg1), bool(args.reg2), acc=acc_l, row_mask_u8=tm_owned)
+                              bool(args.reg1), bool(args.reg2), acc=acc_l, row_mask_u8=tm_owned, edge_state=est_l)
     else:
         loss = ops.fused_loss(random_out, sb.y, tm_full, acc=acc_r, reg1=False, reg2=False, row_mask_u8=tm_owned)
     backward_fn(loss)
