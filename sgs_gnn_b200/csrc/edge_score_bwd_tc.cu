@@ -658,14 +658,14 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     float gs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) gs[k] = 0.f;
-    uint32_t it = 0;
-    for (int64_t s = sub0; s < nsub; s += sstep, ++it) {
-      // all global loads of the stage are issued before the stage slot is waited for
-      int sn[NIT], dn[NIT];
+    // thread -> 16-byte chunk cc of the NIT consecutive rows NIT * (lt_id / CH) + k: consecutive edges mostly share
+    // their source (runs of ~10 in bucket order), whose row chunk is then loaded once
+    const int cc = lt_id % CH;
+    const int row0 = NIT * (lt_id / CH);
+    auto load_idx = [&](int64_t s, int* sn, int* dn) {
 #pragma unroll
       for (int k = 0; k < NIT; ++k) {
-        const int item = lt_id + k * LOAD_THREADS;
-        const int64_t i = s * SUB_M + item / CH;
+        const int64_t i = s * SUB_M + row0 + k;
         sn[k] = -1;
         dn[k] = 0;
         if (i < n) {
@@ -674,15 +674,28 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
           dn[k] = dst[e];
         }
       }
+    };
+    int sn[NIT], dn[NIT], sn2[NIT], dn2[NIT];
+    if (sub0 < nsub) load_idx(sub0, sn, dn);
+    uint32_t it = 0;
+    for (int64_t s = sub0; s < nsub; s += sstep, ++it) {
+      // all global loads of the stage are issued before the stage slot is waited for; the endpoints of the next
+      // stage are prefetched behind them
       uint4 xv[NIT], yv[NIT], av[NDA];
+      bool same = true;
+#pragma unroll
+      for (int k = 1; k < NIT; ++k) same = same && (sn[k] == sn[0]);
 #pragma unroll
       for (int k = 0; k < NIT; ++k) {
-        const int cc = (lt_id + k * LOAD_THREADS) % CH;
         xv[k] = yv[k] = make_uint4(0, 0, 0, 0);
         if (sn[k] >= 0) {
-          xv[k] = *reinterpret_cast<const uint4*>(tab + (int64_t)sn[k] * H + cc * 8);
+          if (k == 0 || !same) xv[k] = *reinterpret_cast<const uint4*>(tab + (int64_t)sn[k] * H + cc * 8);
           yv[k] = *reinterpret_cast<const uint4*>(tab + (int64_t)dn[k] * H + cc * 8);
         }
+      }
+      if (same) {
+#pragma unroll
+        for (int k = 1; k < NIT; ++k) xv[k] = xv[0];
       }
 #pragma unroll
       for (int k = 0; k < NDA; ++k) {
@@ -691,14 +704,14 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         av[k] = make_uint4(0, 0, 0, 0);
         if (i < n) av[k] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + i * H + nb * BN + (item % (BN / 8)) * 8));
       }
+      if (s + sstep < nsub) load_idx(s + sstep, sn2, dn2);
       const uint32_t slot = it % NSTAGE;
       mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
       uint8_t* fst = sm + slot * STAGE;
       uint8_t* dst_da = fst + F_BYTES;
 #pragma unroll
       for (int k = 0; k < NIT; ++k) {
-        const int item = lt_id + k * LOAD_THREADS;
-        const int row = item / CH, cc = item % CH;
+        const int row = row0 + k;
         const uint32_t off = sw128_offset(row, cc & 7);
         *reinterpret_cast<uint4*>(fst + (2 * (cc >> 3)) * (SUB_M * 128) + off) =
             make_uint4(Cvt<T>::mul2(xv[k].x, yv[k].x), Cvt<T>::mul2(xv[k].y, yv[k].y),
@@ -725,11 +738,16 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
           gs[2 * m + 1] += f.y;
         }
       }
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        sn[k] = sn2[k];
+        dn[k] = dn2[k];
+      }
     }
     {
-      const int cc = lt_id % (BN / 8);
+      const int gc = lt_id % (BN / 8);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(gsum_s + cc * 8 + k, gs[k]);
+      for (int k = 0; k < 8; ++k) atomicAdd(gsum_s + gc * 8 + k, gs[k]);
     }
     // all loader warps (everything but the MMA warp) have added their column sums
     asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");

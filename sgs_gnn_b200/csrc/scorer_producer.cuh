@@ -2,7 +2,9 @@
 // out[src], out[dst] of a 128-edge tile with 128-bit loads and writes the [x*y | x-y] feature blocks into the
 // SWIZZLE_128B K-major stage ring consumed by tcgen05.mma.
 //
-// 256 producer threads; thread pt owns 16-byte chunk c = pt & 7 (8 columns) of rows (pt >> 3) + 32*i, i < 4.
+// 256 producer threads; thread pt owns 16-byte chunk c = pt & 7 (8 columns) of the 4 CONSECUTIVE rows
+// 4 * (pt >> 3) + i, i < 4: consecutive edges share their source even in a sampled / bucketed edge list (runs of
+// ~10 edges), so the source row is loaded once for the four.
 // Software pipeline (everything that can miss in L2 is issued at least one stage before it is consumed):
 //   * the edge endpoints (src/dst ids) of tile t+1 are loaded while tile t is being built,
 //   * the row chunks of stage g+1 (possibly the first stage of the next tile) are in flight while stage g is
@@ -30,7 +32,7 @@ struct FeatureProducer {
     Rows r;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int64_t e = t * TILE_M + row_base + 32 * i;
+      int64_t e = t * TILE_M + 4 * row_base + i;
       if (e >= n) e = n - 1;
       if (ids) e = ids[e];
       r.s[i] = src[e];
@@ -80,7 +82,7 @@ struct FeatureProducer {
         uint8_t* stage = stages + slot * STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t off = sw128_offset(row_base + 32 * i, c);
+          const uint32_t off = sw128_offset(4 * row_base + i, c);
           *reinterpret_cast<uint4*>(stage + off) =
               make_uint4(Cvt<T>::mul2(cx[i].x, cy[i].x), Cvt<T>::mul2(cx[i].y, cy[i].y),
                          Cvt<T>::mul2(cx[i].z, cy[i].z), Cvt<T>::mul2(cx[i].w, cy[i].w));
