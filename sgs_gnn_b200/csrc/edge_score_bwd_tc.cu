@@ -306,9 +306,10 @@ edge_score_bwd_da_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
 //   * the gathers of x = tab[src], y = tab[dst] are 64-byte warp-coalesced 16-bit loads (the source row hits L1).
 // A = this kind's columns of diag(w2) W1, resident in smem ([H x 64] blocks, MN-major through the descriptor);
 // B = the G tile [128 e x 128 j] streamed by TMA (SWIZZLE_128B boxes) through a 3-stage ring -- no loader warps.
-// Roles: warp 0 TMA producer, warp 1 MMA issue + TMEM allocation, warps 2-17 epilogue: 4 groups of 4 warps (one
-// warp per TMEM lane quarter); group g drains accumulator buffer g & 1 (every other tile of this CTA), edges
-// [64 (g >> 1), +64) of the tile.
+// Roles: warp 0 TMA producer (lane 0) + endpoint staging (all lanes: the tile's (src | run-start flag, dst) pairs
+// go to shared memory, so the epilogue reads them with one broadcast LDS.64 per edge instead of shuffles),
+// warp 1 MMA issue + TMEM allocation, warps 2-17 epilogue: 4 groups of 4 warps (one warp per TMEM lane quarter);
+// group g drains accumulator buffer g & 1 (every other tile of this CTA), edges [64 (g >> 1), +64) of the tile.
 namespace kbf {
 constexpr int TILE_E = 128;                    // edges per tile (N of the MMA)
 constexpr int CB = 128;                        // node-embedding columns per CTA kind (M of the MMA)
@@ -337,6 +338,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "memory");
 }
 
+// 18 warps = 5 on two of the four SM sub-partitions (16 K registers each): at most 96 registers per thread
 template <typename T, int H>
 __global__ void __launch_bounds__(kbf::THREADS, 1)
 edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __restrict__ tab,
@@ -358,7 +360,7 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* sm = smem_raw + pad;
   const uint32_t sm_addr = raw_addr + pad;
-  constexpr uint32_t kUsed = A_BYTES + NSTAGE * STAGE_BYTES + 16 * 8 + 16;
+  constexpr uint32_t kUsed = A_BYTES + NSTAGE * STAGE_BYTES + 16 * 8 + 16 + 2 * TILE_E * 8;
   {
     uint32_t dyn_size;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
@@ -368,8 +370,9 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
   const uint32_t g_base = a_base + A_BYTES;      // G stage ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + A_BYTES + NSTAGE * STAGE_BYTES);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 16);
+  int2* ep_s = reinterpret_cast<int2*>(sm + A_BYTES + NSTAGE * STAGE_BYTES + 16 * 8 + 16);   // [2][TILE_E]
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t full0 = bar0, empty0 = bar0 + 32, dffull0 = bar0 + 64, dfempty0 = bar0 + 80;
+  const uint32_t full0 = bar0, empty0 = bar0 + 32, dffull0 = bar0 + 64, dfempty0 = bar0 + 80, epfull0 = bar0 + 96;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -386,6 +389,7 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
     for (int s = 0; s < 2; ++s) {
       mbar_init(dffull0 + 8 * s, 1);
       mbar_init(dfempty0 + 8 * s, (EPI_GROUPS / 2) * 4 * 32);
+      mbar_init(epfull0 + 8 * s, 32);
     }
     fence_mbar_init();
   }
@@ -421,10 +425,13 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp == 0) {
-    // ------------------------------- TMA producer: G sub-tiles [128 e x 128 j] -------------------------------
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t t = tile0; t < ntiles; t += tstep) {
+    // --------------- TMA producer (lane 0): G sub-tiles [128 e x 128 j];  endpoint staging (all lanes) ---------------
+    // lane l stages edges 4l .. 4l+3 of the tile as (src | run-start flag << 31, dst): the flag marks an edge whose
+    // source differs from its predecessor's inside the same 64-edge half (the first edge of a half is never
+    // flagged: the epilogue starts a fresh run there).  Dead edges (past n) become (0, 0): their G rows are zero.
+    uint32_t it = 0, lt = 0;
+    for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
+      if (lane == 0) {
 #pragma unroll 1
         for (int js = 0; js < NJ; ++js, ++it) {
           const uint32_t slot = it % NSTAGE;
@@ -436,8 +443,30 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
           tma_load_2d(dst_s + TILE_E * 128, &map_g, full0 + 8 * slot, js * 128 + 64, (int)(t * TILE_E));
         }
       }
+      __syncwarp();
+      int sv[4], dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t i = t * TILE_E + 4 * lane + k;
+        sv[k] = dv[k] = 0;
+        if (i < n) {
+          const int64_t e = ids ? ids[i] : i;
+          sv[k] = src[e];
+          dv[k] = dst[e];
+        }
+      }
+      const int prev = __shfl_up_sync(0xffffffffu, sv[3], 1);
+      const uint32_t tb = lt & 1;
+      mbar_wait(dfempty0 + 8 * tb, ((lt >> 1) & 1) ^ 1);   // the epilogue of tile lt - 2 has read its endpoints
+      int2* ep = ep_s + tb * TILE_E + 4 * lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int before = k == 0 ? prev : sv[k - 1];
+        const bool start = (k != 0 || (lane & 15) != 0) && sv[k] != before;
+        ep[k] = make_int2(sv[k] | (start ? (int)0x80000000u : 0), dv[k]);
+      }
+      mbar_arrive(epfull0 + 8 * tb);
     }
-    __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(Cvt<T>::kFmt, CB, TILE_E) | (1u << 15);  // A is MN-major
@@ -478,75 +507,62 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
     float* doc = d_out + c;
     const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + tb * 256 + eh * 64;
     const float invS = 1.0f / grad_scale(dp_absmax[0]);
-    constexpr int EPL = 64 / 32;                    // edges per lane and tile half
-    int sn[EPL], dn[EPL], sn2[EPL], dn2[EPL];
-    auto load_endpoints = [&](int64_t t, int* s, int* d) {
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) {
-        const int64_t i = t * TILE_E + eh * 64 + 32 * k + lane;
-        s[k] = -1;
-        d[k] = 0;
-        if (i < n) {
-          const int64_t e = ids ? ids[i] : i;
-          s[k] = src[e];
-          d[k] = dst[e];
-        }
-      }
-    };
-    int64_t t = tile0 + tb * tstep;
+    const int2* ep = ep_s + tb * TILE_E + eh * 64;
+    constexpr uint64_t ROWB2 = (uint64_t)H * 2, ROWB4 = (uint64_t)H * 4;
+    const char* tabb = reinterpret_cast<const char*>(tabc);
+    char* docb = reinterpret_cast<char*>(doc);
     uint32_t lt = tb;
-    if (t < ntiles) load_endpoints(t, sn, dn);
-    for (; t < ntiles; t += 2 * tstep, lt += 2) {
-      // the endpoints of this group's next tile are in flight while this one is reduced
-      if (t + 2 * tstep < ntiles) load_endpoints(t + 2 * tstep, sn2, dn2);
+    for (int64_t t = tile0 + tb * tstep; t < ntiles; t += 2 * tstep, lt += 2) {
+      mbar_wait(epfull0 + 8 * tb, (lt >> 1) & 1);
+      // software pipeline over chunks of CHUNK edges: the endpoints and the x / y gathers of chunk ch + 1 are
+      // issued before chunk ch is reduced, so the gather latency overlaps the FMAs / REDs of the previous chunk
+      constexpr int NCH = 64 / CHUNK;
+      // (the endpoints are re-read from shared memory when a chunk is reduced: one LDS.64 per edge is cheaper than
+      // keeping two chunks of them in registers -- 96 registers per thread, see above)
+      unsigned short xv[2][CHUNK], yv[2][CHUNK];
+      auto issue = [&](int ch, unsigned short* xc, unsigned short* yc) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          const int2 sd = ep[ch * CHUNK + j];
+          xc[j] = __ldg(reinterpret_cast<const unsigned short*>(tabb + (uint32_t)(sd.x & 0x7FFFFFFF) * ROWB2));
+          yc[j] = __ldg(reinterpret_cast<const unsigned short*>(tabb + (uint32_t)sd.y * ROWB2));
+        }
+      };
+      issue(0, xv[0], yv[0]);
+      uint32_t cur_s = (uint32_t)ep[0].x;           // never flagged (first edge of the half)
+      float xcur = tab_to_float<T>(xv[0][0]);
+      float acc = 0.f;                              // S-scaled source-side run sum
       mbar_wait(dffull0 + 8 * tb, (lt >> 1) & 1);
       tc_fence_after();
-      int cur_s = __shfl_sync(0xffffffffu, sn[0], 0);
-      float acc = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 64 / CHUNK; ++ch) {
-        constexpr int CPL = 32 / CHUNK;             // chunks per endpoint register
-        const int k = ch / CPL, bl = (ch % CPL) * CHUNK;
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int cb = ch & 1;
         uint32_t f1[CHUNK], f2[CHUNK];
         tmem_ld8(taddr0 + ch * CHUNK, f1);
         tmem_ld8(taddr0 + 128 + ch * CHUNK, f2);
-        int s[CHUNK], d[CHUNK];
-        unsigned short xv[CHUNK], yv[CHUNK];
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          s[j] = __shfl_sync(0xffffffffu, sn[k], bl + j);
-          d[j] = __shfl_sync(0xffffffffu, dn[k], bl + j);
-        }
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          xv[j] = __ldg(tabc + (int64_t)(s[j] < 0 ? 0 : s[j]) * H);
-          yv[j] = __ldg(tabc + (int64_t)d[j] * H);
-        }
+        if (ch + 1 < NCH) issue(ch + 1, xv[cb ^ 1], yv[cb ^ 1]);
         tmem_ld_wait();
-        if (ch == 64 / CHUNK - 1) {  // this warp has read all of its part of the accumulator
+        int2 sd[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) sd[j] = ep[ch * CHUNK + j];
+        if (ch == NCH - 1) {  // this warp has read all of its part of the accumulator and of the endpoints
           tc_fence_before();
           mbar_arrive(dfempty0 + 8 * tb);
         }
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) {
-          if (s[j] != cur_s) {          // warp-uniform: a new run of equal sources starts
-            if (cur_s >= 0) atomicAdd(doc + (int64_t)cur_s * H, acc);
+          if (sd[j].x < 0) {            // warp-uniform: a new run of equal sources starts
+            atomicAdd(reinterpret_cast<float*>(docb + cur_s * ROWB4), acc * invS);
             acc = 0.f;
-            cur_s = s[j];
+            cur_s = (uint32_t)sd[j].x & 0x7FFFFFFFu;
+            xcur = tab_to_float<T>(xv[cb][j]);
           }
-          if (s[j] >= 0) {              // live edge (warp-uniform)
-            const float a = __uint_as_float(f1[j]) * invS, b = __uint_as_float(f2[j]) * invS;
-            acc += fmaf(a, tab_to_float<T>(yv[j]), b);
-            atomicAdd(doc + (int64_t)d[j] * H, fmaf(a, tab_to_float<T>(xv[j]), -b));
-          }
+          const float a = __uint_as_float(f1[j]), b = __uint_as_float(f2[j]);
+          acc += fmaf(a, tab_to_float<T>(yv[cb][j]), b);
+          atomicAdd(reinterpret_cast<float*>(docb + (uint32_t)sd[j].y * ROWB4), fmaf(a, xcur, -b) * invS);
         }
       }
-      if (cur_s >= 0) atomicAdd(doc + (int64_t)cur_s * H, acc);
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) {
-        sn[k] = sn2[k];
-        dn[k] = dn2[k];
-      }
+      atomicAdd(reinterpret_cast<float*>(docb + cur_s * ROWB4), acc * invS);
     }
   }
 
@@ -947,8 +963,10 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
       set_error("sgs_edge_score_bwd: cuTensorMapEncodeTiled failed");
       return SGS_E_CUDA;
     }
-    constexpr size_t used = (size_t)2 * 2 * H * 128 + kbf::NSTAGE * kbf::STAGE_BYTES + 16 * 8 + 16;
-    const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;
+    constexpr size_t used =
+        (size_t)2 * 2 * H * 128 + kbf::NSTAGE * kbf::STAGE_BYTES + 16 * 8 + 16 + 2 * kbf::TILE_E * 8;
+    static_assert(used <= 232448, "BF shared memory");
+    const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;   // the kernel traps if its alignment pad does not fit
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_for(H / 128, ntiles), kbf::THREADS, smem, st>>>(map_g, tab, src, dst, ids, n, W1, w2, absmax, d_out);
     SGS_LAUNCH_CHECK();
