@@ -119,26 +119,55 @@ topq_hist_kernel(const uint32_t* __restrict__ keys, int64_t E, unsigned long lon
     if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
 }
 
-// One block.  Walk the histogram from the top bin down to the bin holding the k-th largest key.
-__global__ void topq_find_kernel(unsigned long long* __restrict__ hist, long long* __restrict__ state,
-                                 long long k_total, int level) {
+// One block of 1024 threads: the bin holding the k-th largest key, by a block-wide suffix scan of the histogram
+// (the bin b >= 1, scanning down from the top, with  #keys above b < k <= #keys above b + hist[b];  bin 0 if none).
+__global__ void __launch_bounds__(1024)
+topq_find_kernel(unsigned long long* __restrict__ hist, long long* __restrict__ state, long long k_total,
+                 int level) {
+  __shared__ long long warp_tot[32];
   __shared__ long long s_bin, s_rem, s_cnt;
-  if (threadIdx.x == 0) {
-    long long k = (level == 0) ? k_total : state[1];
-    const int nb = level_bins(level);
-    long long cum = 0;
-    int b = nb - 1;
-    for (; b > 0; --b) {
-      const long long c = (long long)hist[b];
-      if (cum + c >= k) break;
-      cum += c;
+  const int nb = level_bins(level);
+  const int per = nb >= 1024 ? nb / 1024 : 1;          // bins per thread (2 or 1)
+  const int b0 = threadIdx.x * per;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long k = (level == 0) ? k_total : state[1];
+  long long c[2] = {0, 0};
+  if (b0 < nb) {
+    c[0] = (long long)hist[b0];
+    if (per == 2) c[1] = (long long)hist[b0 + 1];
+  }
+  if (threadIdx.x == 0) s_bin = -1;
+  // suffix sums over threads: above = number of keys in bins owned by higher threads
+  long long v = c[0] + c[1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  if (lane == 0) warp_tot[wid] = v;
+  __syncthreads();
+  long long above = v - (c[0] + c[1]);
+  for (int w = wid + 1; w < 32; ++w) above += warp_tot[w];
+  if (b0 < nb) {
+    long long cum = above;
+    for (int j = per - 1; j >= 0; --j) {
+      const int b = b0 + j;
+      const bool hit = (k <= 0) ? (b == nb - 1) : (b >= 1 && cum < k && cum + c[j] >= k);
+      if (hit) {
+        s_bin = b;
+        s_rem = k - cum;   // how many keys to take from bin b (>= 1 when k >= 1)
+        s_cnt = c[j];
+      }
+      cum += c[j];
     }
-    s_bin = b;
-    s_rem = k - cum;  // how many keys to take from bin b (>= 1 when k >= 1)
-    s_cnt = (long long)hist[b];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (s_bin < 0) {       // fewer than k keys above bin 0: everything comes from bin 0 downwards
+      s_bin = 0;
+      s_rem = k - (above + c[1]);
+      s_cnt = c[0];
+    }
     const long long prefix = ((level == 0) ? 0 : state[0]) | (s_bin << level_shift(level));
     state[0] = prefix;
     state[1] = s_rem;
@@ -149,6 +178,7 @@ __global__ void topq_find_kernel(unsigned long long* __restrict__ hist, long lon
       state[6] = s_cnt;            // # keys equal to tau
     }
   }
+  __syncthreads();   // every thread has read its bins
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0ull;
 }
 
@@ -496,7 +526,7 @@ int32_t sgs_topq_keys(const float* p, const float* prob, const float* noise, int
 
 int32_t sgs_topq_find(int64_t* hist, int64_t* state, int64_t k_total, int32_t level, sgs_stream_t stream) {
   SGS_CHECK_ARG(hist && state && level >= 0 && level <= 2 && k_total >= 1, "bad arguments");
-  topq_find_kernel<<<1, 256, 0, as_stream(stream)>>>((unsigned long long*)hist, (long long*)state, k_total, level);
+  topq_find_kernel<<<1, 1024, 0, as_stream(stream)>>>((unsigned long long*)hist, (long long*)state, k_total, level);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }
