@@ -339,7 +339,7 @@ def run_gpu_arm(a):
     if not a.no_e2e:
         host = batch.to("cpu").pin_memory()
         host._sgs_has_train = True
-        h2d = host.nbytes()
+        h2d = host.upload_nbytes() if hasattr(host, "upload_nbytes") else host.nbytes()   # this rank's PCIe bytes
         loader_h = [host]
         for w in range(min(a.warmup, 2)):
             epoch(loader_h, 1)

@@ -90,6 +90,24 @@ class Comm:
                 dist.all_gather(list(full.split(sizes)), full[lo:hi].clone(), group=self.group)
         return full
 
+    def upload_replicated(self, host, dev):
+        """Device copy of a host tensor that every rank holds (the replicated node features): each rank sends only
+        its 1/world row slice over PCIe and the slices are all-gathered over NVLink -- the host link carries the
+        tensor once per box instead of once per GPU."""
+        n = host.size(0)
+        if self.world == 1 or self.staged or n < self.world:
+            return host.to(dev)
+        chunk = (n + self.world - 1) // self.world
+        lo, hi = min(self.rank * chunk, n), min((self.rank + 1) * chunk, n)
+        full = torch.empty((self.world * chunk,) + tuple(host.shape[1:]), dtype=host.dtype, device=dev)
+        mine = full[self.rank * chunk:(self.rank + 1) * chunk]
+        mine[: hi - lo].copy_(host[lo:hi], non_blocking=True)
+        with _timed("comm_exchange"):
+            dist.all_gather_into_tensor(full, mine.clone(), group=self.group)
+        if os.environ.get("SGS_CHECK_UPLOAD"):   # debug aid: the gathered copy must equal a plain full upload
+            assert torch.equal(full[:n], host.to(dev)), "upload_replicated mismatch"
+        return full[:n]
+
     def reduce_rows(self, full, bounds):
         """Sum of `full` over ranks, returned for this rank's owned rows only ([hi-lo, ...])."""
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
@@ -230,11 +248,11 @@ class ShardedBatch:
                                      self.gid, self.num_edges_global)
         return self._local
 
-    def _map(self, fn):
+    def _map(self, fn, fn_x=None):
         o = ShardedBatch(None, self.comm)
         for k in self._TENSORS:
             v = getattr(self, k, None)
-            setattr(o, k, fn(v) if v is not None else None)
+            setattr(o, k, ((fn_x if (k == "x" and fn_x is not None) else fn)(v)) if v is not None else None)
         o.num_classes, o.num_edges_global, o.bounds = self.num_classes, self.num_edges_global, self.bounds
         o._sgs_has_train = self._sgs_has_train
         return o
@@ -243,7 +261,10 @@ class ShardedBatch:
         dev = torch.device(device)
         if self.x.device == dev or (dev.type == "cuda" and dev.index is None and self.x.device.type == "cuda"):
             return self
-        return self._map(lambda t: t.to(dev, non_blocking=non_blocking))
+        fn_x = None
+        if dev.type == "cuda" and self.x.device.type == "cpu" and self.comm is not None and self.comm.world > 1:
+            fn_x = lambda t: self.comm.upload_replicated(t, dev)   # replicated features: PCIe once per box
+        return self._map(lambda t: t.to(dev, non_blocking=non_blocking), fn_x)
 
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())
@@ -251,6 +272,16 @@ class ShardedBatch:
     def nbytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size()
                    for k in self._TENSORS if getattr(self, k, None) is not None)
+
+    def upload_nbytes(self):
+        """Bytes this rank sends over the host link in `.to(cuda)`: everything but the other ranks' slices of x."""
+        w = self.comm.world if self.comm is not None else 1
+        nb = self.nbytes()
+        if w > 1 and not self.comm.staged and self.x.size(0) >= w:
+            chunk = (self.x.size(0) + w - 1) // w
+            rows = max(0, min((self.comm.rank + 1) * chunk, self.x.size(0)) - self.comm.rank * chunk)
+            nb -= (self.x.size(0) - rows) * self.x[0].numel() * self.x.element_size()
+        return nb
 
 
 # ------------------------------------------------------------------------------------------
