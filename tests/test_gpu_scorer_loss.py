@@ -99,3 +99,31 @@ def test_reg1_skipped_when_at_most_one_positive_label(dev):
     loss = ops.fused_loss(logits, y, tm.view(torch.uint8), p_s, ops.graph_of(s_ei, n), 1.0, 0.5, True, True)
     want = ox.hybrid_loss(logits.detach().cpu(), p_s.detach().cpu(), s_ei.cpu(), y.cpu(), tm.cpu())
     assert abs(loss.item() - float(want)) < 1e-5
+
+
+@pytest.mark.parametrize("c,q,n", [(3, 1, 40), (16, 15, 50), (17, 16, 64), (33, 1000, 300), (41, 4097, 700), (49, 333, 90),
+                                   (64, 2049, 400), (70, 500, 100)])
+def test_fused_edge_loss_class_counts_vs_oracle(dev, c, q, n):
+    """One-sweep edge loss (sgs_loss_fwd_fused / _bwd_fused; C <= 64) and the two-kernel path (C = 70) against the
+    fp64 torch restatement of training_hybrid.py:103-132, for every columns-per-lane template and ragged q."""
+    from sgs_gnn_b200 import ops
+    g = torch.Generator().manual_seed(c * 1000 + q)
+    logits_c = torch.randn(n, c, generator=g)
+    y_c = torch.randint(0, c, (n,), generator=g)
+    tm_c = torch.rand(n, generator=g) < 0.7
+    src = torch.sort(torch.randint(0, n, (q,), generator=g)).values          # ascending sources, like a sampled list
+    dst = torch.randint(0, n, (q,), generator=g)
+    s_ei_c = torch.stack([src, dst])
+    p_c = torch.rand(q, generator=g) * 0.98 + 0.01
+    ref_l = logits_c.double().requires_grad_(True)
+    ref_p = p_c.double().requires_grad_(True)
+    want = ox.hybrid_loss(ref_l, ref_p, s_ei_c, y_c, tm_c, True, True, 0.7, 0.4)
+    rg = torch.autograd.grad(want, [ref_l, ref_p])
+    logits = logits_c.to(dev).requires_grad_(True)
+    p_s = p_c.to(dev).requires_grad_(True)
+    loss = ops.fused_loss(logits, y_c.to(dev), tm_c.to(dev).view(torch.uint8), p_s, ops.graph_of(s_ei_c.to(dev), n),
+                          0.7, 0.4, True, True)
+    assert abs(loss.item() - float(want.detach())) <= 2e-5 * max(1.0, abs(float(want.detach())))
+    gl, gp = torch.autograd.grad(loss, [logits, p_s])
+    assert relerr(gl.cpu().double(), rg[0]) < RTOL
+    assert relerr(gp.cpu().double(), rg[1]) < RTOL

@@ -111,11 +111,16 @@ def _emulated_grads(prec, out, ei, W1, b1, w2, b2, gup, keep, p_drop):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
-@pytest.mark.parametrize("h,e,subset,p_drop", [(256, 128, False, 0.0), (256, 5000, False, 0.3), (128, 3333, True, 0.3),
-                                               (256, 20011, True, 0.0)])
-def test_scorer_tc_backward(dev, prec, h, e, subset, p_drop):
+@pytest.mark.parametrize("h,e,subset,p_drop,n_nodes", [
+    (256, 128, False, 0.0, 600), (256, 5000, False, 0.3, 600), (128, 3333, True, 0.3, 600), (256, 20011, True, 0.0, 600),
+    # around the CTA-pair threshold of BA (n >= 256 edges) and single-edge lists
+    (256, 255, False, 0.3, 600), (256, 256, False, 0.0, 600), (256, 257 * 3, True, 0.3, 600), (256, 1, False, 0.0, 600),
+    (128, 1, False, 0.3, 600),
+    # more nodes than one destination bucket holds (2^15 rows at H = 256, 2^16 at H = 128): the stable
+    # destination-range partition of the edge list is exercised
+    (256, 30000, True, 0.3, 100000), (128, 9000, False, 0.0, 140000)])
+def test_scorer_tc_backward(dev, prec, h, e, subset, p_drop, n_nodes):
     from sgs_gnn_b200 import ops, rng
-    n_nodes = 600
     ei, out, W1, b1, w2, b2 = _setup(n_nodes, e, h, h + e + 1)
     graph = ops.graph_of(ei.to(dev), n_nodes)
     g = torch.Generator().manual_seed(3)
