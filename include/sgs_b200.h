@@ -72,6 +72,14 @@ size_t sgs_csr_workspace_bytes(int64_t M, int64_t N);
 int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64_t N,
                       int32_t* rowptr, int32_t* perm, int32_t* nbr, int32_t* order, void* ws,
                       size_t ws_bytes, sgs_stream_t stream);
+/* Same outputs for an edge list whose `key` column is ALREADY non-decreasing (e.g. the by-source view of
+ * edges selected in ascending id from a (src,dst)-sorted edge_index): no sort -- rowptr by binary search,
+ * perm = identity, nbr = other.  The caller vouches for the order; sgs_keys_unsorted checks it on the device
+ * (flag[0] = 1 if some key[i] > key[i+1]). */
+int32_t sgs_csr_build_sorted(const int32_t* key, const int32_t* other, int64_t M, int64_t N,
+                             int32_t* rowptr, int32_t* perm, int32_t* nbr, int32_t* order, void* ws,
+                             size_t ws_bytes, sgs_stream_t stream);
+int32_t sgs_keys_unsorted(const int32_t* key, int64_t M, int32_t* flag, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3a gcn_norm  (PyG gcn_norm + add_remaining_self_loops as called from model.py:107-111,

@@ -29,6 +29,8 @@ SIGNATURES = {
     "sgs_edge_index_gather": (I32, [P, I64, P, I64, P, P, P, P]),
     "sgs_csr_workspace_bytes": (SZ, [I64, I64]),
     "sgs_csr_build": (I32, [P, P, I64, I64, P, P, P, P, P, SZ, P]),
+    "sgs_csr_build_sorted": (I32, [P, P, I64, I64, P, P, P, P, P, SZ, P]),
+    "sgs_keys_unsorted": (I32, [P, I64, P, P]),
     "sgs_gcn_norm": (I32, [P, P, P, P, I64, I64, P, P, P, P, P]),
     "sgs_gcn_norm_apply": (I32, [P, P, P, P, P, I64, I64, P, P]),
     "sgs_spmm": (I32, [P, P, P, P, P, P, P, I64, I64, P, P, I32, F32, U64, P]),

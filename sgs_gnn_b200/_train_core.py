@@ -74,7 +74,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     if args.conditional or args.sparse_edge_mlp:
         # training_hybrid.py:45-48
         r = sampling.sample_random(_softmax_prob(batch.prob), q, validate=False)
-        g_rand = g_full.subgraph(r.sel)
+        g_rand = g_full.subgraph(r.sel, ascending=True)
 
     # pass 1: probabilities of ALL edges (training_hybrid.py:51-64), no autograd tape
     profiler = getattr(model, "gpu_profiler", None)
@@ -95,7 +95,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
 
     # sample (training_hybrid.py:72-83)
     smp = sampling.sample_edges(p_full, batch.prob, q, False, coef, validate=False)
-    g_s = g_full.subgraph(smp.sel)
+    g_s = g_full.subgraph(smp.sel, ascending=True)
     if pipeline == "hybrid":
         # edge_probs_full[mask] with grad (training_hybrid.py:86): backward over the q edges only
         p_sel = ops.gather_selected(p_full, None, smp.sel, ops.SAMPLE_RAW, 0.0, None)[0]
@@ -237,7 +237,7 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
                 ei = sampling.random_edge_sampling(ei, q=q)
             elif mode == "edge" and ei.shape[1] > q:
                 g_full = ops.graph_of(batch.edge_index, batch.x.size(0))
-                ei = g_full.subgraph(sampling.sample_random(_softmax_prob(batch.prob), q).sel)
+                ei = g_full.subgraph(sampling.sample_random(_softmax_prob(batch.prob), q).sel, ascending=True)
             out = model(batch, ei)
             loss = _ce(criterion, out, batch, batch.train_mask.view(torch.uint8))
             _backward(loss)

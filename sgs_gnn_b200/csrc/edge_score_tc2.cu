@@ -216,29 +216,40 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
     float acc_b2 = 0.f;
     const uint32_t tempty_leader0 = mapa_shared(tempty0, 0);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16);
+    // per-row inputs of the NEXT tile (dropout key id; MODE 1: dz, p) are loaded one tile ahead: their latency (an
+    // HBM miss each) would otherwise sit on the epilogue's critical path once per tile
+    int64_t kid_n = 0;
+    float dz_n = 0.f, pe_n = 0.f;
+    auto prefetch_row = [&](int64_t t) {
+      const int64_t i = t * TILE_M + r;
+      if (drop) {
+        int64_t e = i < n ? i : n - 1;
+        if (key_ids) e = key_ids[e];   // the edge list was re-ordered by the caller: original ids for the mask
+        else if (ids) e = ids[e];
+        kid_n = e;
+      }
+      if (MODE == 1) {
+        dz_n = 0.f;
+        if (i < n) {
+          dz_n = dp[i];
+          if (p_fwd) pe_n = p_fwd[i];
+        }
+      }
+    };
     uint32_t lt = grp;
+    if (tile0 + grp * tstep < ntiles_padded) prefetch_row(tile0 + grp * tstep);
     for (int64_t t = tile0 + grp * tstep; t < ntiles_padded; t += EPI_GROUPS * tstep, lt += EPI_GROUPS) {
       const uint32_t acc = lt & 1;
       const uint32_t tempty_leader = tempty_leader0 + 8 * acc;
       const uint32_t taddr = taddr0 + acc * H;
       const int64_t i = t * TILE_M + r;
-      uint32_t rowkey = 0;
-      if (drop) {
-        int64_t e = i < n ? i : n - 1;
-        if (key_ids) e = key_ids[e];   // the edge list was re-ordered by the caller: original ids for the mask
-        else if (ids) e = ids[e];
-        rowkey = dropout_rowkey(seed, (uint64_t)e);
-      }
+      const int64_t kid = kid_n;
+      float dz = dz_n;
+      if (MODE == 1 && p_fwd) dz *= pe_n * (1.0f - pe_n);   // p_fwd == nullptr: dp already holds dz = dp * p * (1 - p)
+      if (t + EPI_GROUPS * tstep < ntiles_padded) prefetch_row(t + EPI_GROUPS * tstep);
+      const uint32_t rowkey = drop ? dropout_rowkey(seed, (uint64_t)kid) : 0u;
       uint32_t g_lo = 0, g_hi = 0;   // MODE 1: this row's gate gradient in the low / high 16 bits
       if (MODE == 1) {
-        float dz = 0.f;
-        if (i < n) {
-          dz = dp[i];   // p_fwd == nullptr: the caller passes dz = dp * p * (1 - p) itself
-          if (p_fwd) {
-            const float pe = p_fwd[i];
-            dz *= pe * (1.0f - pe);
-          }
-        }
         acc_b2 += dz;
         const float g = dz * gscale;
         const uint32_t gg = Cvt<T>::pack(g, g);

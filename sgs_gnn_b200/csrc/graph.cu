@@ -48,6 +48,26 @@ __global__ void iota_copy_kernel(const int32_t* __restrict__ key, int64_t M, int
   }
 }
 
+// flag[0] |= 1 if keys are not non-decreasing
+__global__ void unsorted_flag_kernel(const int32_t* __restrict__ key, int64_t M, int32_t* __restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i + 1 < M; i += stride) bad |= key[i] > key[i + 1];
+  if (bad) *flag = 1;
+}
+
+// perm = identity, nbr = other  (CSR of an edge list whose keys are already sorted)
+__global__ void iota_nbr_kernel(const int32_t* __restrict__ other, int64_t M, int32_t* __restrict__ perm,
+                                int32_t* __restrict__ nbr) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < M; i += stride) {
+    perm[i] = (int32_t)i;
+    nbr[i] = other[i];
+  }
+}
+
 // rowptr[k] = first position in the sorted key array with key >= k   (k in [0, N])
 __global__ void rowptr_kernel(const int32_t* __restrict__ sorted, int64_t M, int64_t N,
                               int32_t* __restrict__ rowptr) {
@@ -200,6 +220,40 @@ int32_t sgs_csr_build(const int32_t* key, const int32_t* other, int64_t M, int64
   SGS_CUDA(cudaMemcpyAsync(perm, dv.Current(), M * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   gather_i32_kernel<<<grid_for(M, 256), 256, 0, st>>>(other, dv.Current(), M, nbr);
   SGS_LAUNCH_CHECK();
+  if (order) return degree_order(rowptr, N, order, ws, ws_bytes, st);
+  return SGS_OK;
+}
+
+int32_t sgs_keys_unsorted(const int32_t* key, int64_t M, int32_t* flag, sgs_stream_t stream) {
+  SGS_CHECK_ARG(M >= 0 && flag, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  SGS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+  if (M < 2) return SGS_OK;
+  SGS_CHECK_ARG(key != nullptr, "null pointer");
+  unsorted_flag_kernel<<<grid_for(M, 256), 256, 0, st>>>(key, M, flag);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_csr_build_sorted(const int32_t* key, const int32_t* other, int64_t M, int64_t N, int32_t* rowptr,
+                             int32_t* perm, int32_t* nbr, int32_t* order, void* ws, size_t ws_bytes,
+                             sgs_stream_t stream) {
+  SGS_CHECK_ARG(M >= 0 && N > 0, "bad sizes");
+  SGS_CHECK_ARG(rowptr != nullptr, "null rowptr");
+  cudaStream_t st = as_stream(stream);
+  if (ws_bytes < sgs_csr_workspace_bytes(M, N) || !ws) {
+    set_error("sgs_csr_build_sorted: workspace too small");
+    return SGS_E_WORKSPACE;
+  }
+  if (M == 0) {
+    SGS_CUDA(cudaMemsetAsync(rowptr, 0, (N + 1) * sizeof(int32_t), st));
+  } else {
+    SGS_CHECK_ARG(key && other && perm && nbr, "null pointer");
+    rowptr_kernel<<<(unsigned)ceil_div(N + 1, 256), 256, 0, st>>>(key, M, N, rowptr);
+    SGS_LAUNCH_CHECK();
+    iota_nbr_kernel<<<grid_for(M, 256), 256, 0, st>>>(other, M, perm, nbr);
+    SGS_LAUNCH_CHECK();
+  }
   if (order) return degree_order(rowptr, N, order, ws, ws_bytes, st);
   return SGS_OK;
 }

@@ -35,7 +35,7 @@ def _member_logits(args, model, batch, q, mode, cache):
             r = sampling.sample_edges(p_full, None, q, True, args.degree_bias_coef, validate=True)
             # sampled_edge_weight = (p * st)[mask].clamp(0, 1), istest (sampling.py:94,137-155)
             w = ops.gather_selected(p_full, None, r.sel, SAMPLE_TEST, args.degree_bias_coef, r.S, True)[1]
-            return model(batch, g_full.subgraph(r.sel), w)
+            return model(batch, g_full.subgraph(r.sel, ascending=True), w)
         return model(batch, ei)
     if mode == "random":
         if e > q:
@@ -45,7 +45,7 @@ def _member_logits(args, model, batch, q, mode, cache):
         if e > q:
             g_full = ops.graph_of(ei, n)
             r = sampling.sample_random(_softmax_prob(batch.prob), q)
-            return model(batch, g_full.subgraph(r.sel))
+            return model(batch, g_full.subgraph(r.sel, ascending=True))
         return model(batch, ei)
     if mode == "full":
         return model(batch, ei)

@@ -199,6 +199,7 @@ class Graph:
         self.edge_index = edge_index
         self._csr_dst = None
         self._csr_src = None
+        self._src_sorted = None   # is `src` non-decreasing?  (None: not checked yet)
         self._norm_unw = None
         self._norm_w = None  # (weakref to weight tensor, version, GcnNorm)
 
@@ -217,8 +218,20 @@ class Graph:
             raise RuntimeError("edge_index contains node ids outside [0, num_nodes)")
         return Graph(src, dst, num_nodes, ei)
 
-    def subgraph(self, ids, want_edge_index=False):
-        """Edge-induced subgraph on edge ids (int32 [q]); optionally also the int64 [2,q] tensor."""
+    @property
+    def src_sorted(self):
+        """True when the source column is non-decreasing (PyG edge lists are (src,dst)-sorted): checked on the
+        device once per graph (one 4-byte read)."""
+        if self._src_sorted is None:
+            flag = torch.empty(1, dtype=torch.int32, device=self.device)
+            check(lib().sgs_keys_unsorted(_p(self.src), self.num_edges, _p(flag), _stream()), "sgs_keys_unsorted")
+            self._src_sorted = int(flag.item()) == 0
+        return self._src_sorted
+
+    def subgraph(self, ids, want_edge_index=False, ascending=False):
+        """Edge-induced subgraph on edge ids (int32 [q]); optionally also the int64 [2,q] tensor.  `ascending`: the
+        caller vouches that ids ascend (the sampler's compaction order) -- the subgraph of a source-sorted graph is
+        then source-sorted too and its by-source CSR needs no sort."""
         q = int(ids.numel())
         src = _vec(q, torch.int32, self.device)
         dst = _vec(q, torch.int32, self.device)
@@ -231,9 +244,12 @@ class Graph:
             src, dst = self.src[idl].contiguous(), self.dst[idl].contiguous()
             if want_edge_index:
                 out = torch.stack([src.long(), dst.long()])
-        return Graph(src, dst, self.num_nodes, out)
+        g = Graph(src, dst, self.num_nodes, out)
+        if ascending and self.src_sorted:
+            g._src_sorted = True
+        return g
 
-    def _build(self, key, other):
+    def _build(self, key, other, presorted=False):
         n, m = self.num_nodes, self.num_edges
         rowptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
         perm = _vec(max(m, 1), torch.int32, self.device)
@@ -241,9 +257,10 @@ class Graph:
         order = torch.empty(n + 1, dtype=torch.int32, device=self.device)   # [N] = number of hub rows
         nbytes = lib().sgs_csr_workspace_bytes(m, n)
         ws = _ws(nbytes, self.device, "csr_build")
+        fn = lib().sgs_csr_build_sorted if presorted else lib().sgs_csr_build
         with _timed("csr_build"):
-            check(lib().sgs_csr_build(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(order), _p(ws),
-                                      ws.numel(), _stream()), "sgs_csr_build")
+            check(fn(_p(key), _p(other), m, n, _p(rowptr), _p(perm), _p(nbr), _p(order), _p(ws), ws.numel(),
+                     _stream()), "sgs_csr_build")
         return rowptr, perm, nbr, order
 
     @property
@@ -255,7 +272,8 @@ class Graph:
     @property
     def csr_src(self):
         if self._csr_src is None:
-            self._csr_src = self._build(self.src, self.dst)
+            # only a hint that was already established is used here (no device read on this path)
+            self._csr_src = self._build(self.src, self.dst, presorted=self._src_sorted is True)
         return self._csr_src
 
     def norm(self, edge_weight=None):

@@ -151,7 +151,7 @@ class LocalGraph:
 
     def subgraph(self, ids):
         gid = self.gid[ids.long()] if self.gid is not None else None
-        return LocalGraph(self.graph.subgraph(ids), self.bounds, self.comm, gid)
+        return LocalGraph(self.graph.subgraph(ids, ascending=True), self.bounds, self.comm, gid)
 
     def norm(self, edge_weight=None):
         if edge_weight is None:

@@ -162,3 +162,27 @@ def test_golden_gnn_forward(dev):
         lu = model(D, rei)
     assert relerr(lw.cpu(), t(z["logits_weighted"])) < RTOL
     assert relerr(lu.cpu(), t(z["logits_unweighted"])) < RTOL
+
+
+def test_presorted_by_source_csr_equals_sorted_build(dev):
+    """Ascending-id subgraphs of a (src,dst)-sorted edge list skip the by-source sort (sgs_csr_build_sorted):
+    rowptr / perm / nbr / row order must equal the radix-sort build bit for bit; an unsorted parent keeps the sort."""
+    from sgs_gnn_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n, e = 3000, 40000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    key = ei[0] * n + ei[1]
+    ei = ei[:, torch.argsort(key, stable=True)].contiguous()
+    full = ops.graph_of(ei.to(dev), n)
+    assert full.src_sorted
+    ids = torch.sort(torch.randperm(e, generator=g)[:9000]).values.int().to(dev)
+    fast = full.subgraph(ids, ascending=True)
+    assert fast._src_sorted is True
+    slow = ops.Graph(fast.src.clone(), fast.dst.clone(), n)
+    for a, b in zip(fast.csr_src, slow.csr_src):
+        assert torch.equal(a, b)
+    for a, b in zip(fast.csr_dst, slow.csr_dst):
+        assert torch.equal(a, b)
+    shuffled = ops.graph_of(ei[:, torch.randperm(e, generator=g)].contiguous().to(dev), n)
+    assert not shuffled.src_sorted
+    assert shuffled.subgraph(ids, ascending=True)._src_sorted is None
