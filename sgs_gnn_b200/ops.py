@@ -450,7 +450,11 @@ class GCNConvFn(torch.autograd.Function):
             if need_w:  # dW[d, fin] = dh^T x
                 dw = gemm_tn(dh, x, static_b=not x.requires_grad)
             if need_x:  # dx[n, fin] = dh W
-                dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d, precision=PREC_FP32)
+                if _state["gemm"] != PREC_FP32:
+                    # NT form on tcgen05 against the (tiny) transposed weight: dh W = dh (W^T)^T
+                    dx = linear_nt(dh, weight.t().contiguous(), precision=PREC_TF32)
+                else:
+                    dx = gemm(dh, d, 1, weight, 1, fin, n, fin, d, precision=PREC_FP32)
         if need_ew and ctx.has_w:
             m = graph.num_edges
             dew = _vec(m, torch.float32, g.device)

@@ -364,7 +364,10 @@ class ShardedGCNConvFn(torch.autograd.Function):
             if need_x:
                 dx = torch.zeros(n, fin, dtype=torch.float32, device=gout.device)
                 if ns > 0:
-                    ops.gemm(dh_slab, d, 1, weight, 1, fin, ns, fin, d, out=dx[lo:hi], precision=PREC_FP32)
+                    if ops._state["gemm"] != PREC_FP32:   # dh W = dh (W^T)^T: NT form on tcgen05
+                        ops.linear_nt_into(dh_slab, weight.t().contiguous(), dx[lo:hi])
+                    else:
+                        ops.gemm(dh_slab, d, 1, weight, 1, fin, ns, fin, d, out=dx[lo:hi], precision=PREC_FP32)
         if need_ew and ctx.has_w:
             m = g.num_edges
             dew = ops._vec(m, torch.float32, gout.device, zero=True)
