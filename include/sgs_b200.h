@@ -100,12 +100,14 @@ int32_t sgs_gcn_norm_apply(const int32_t* rowptr, const int32_t* perm, const int
  * K3b SpMM  (PyG propagate: index_select + mul + scatter_add, model.py:107-111,159-161).
  * out[r,:] = act( sum_{i in [rowptr[r],rowptr[r+1])} what[i]*h[nbr[i],:] + selfw*h[r,:] + bias )
  * with selfw = dis[r]^2*loopw[r] (pass dis = NULL for no self term).  flags: bit0 = ReLU,
- * bit1 = dropout(p_drop, seed) after ReLU, bit2 = accumulate into out.
+ * bit1 = dropout(p_drop, seed) after ReLU, bit2 = accumulate into out (after the activation), bit3 = out holds a
+ * root term that joins the sum inside the activation.
  * Atomic-free segment reduction; one warp (or several for hub rows) per destination row.
  * ---------------------------------------------------------------------------------------- */
 #define SGS_SPMM_RELU 1
 #define SGS_SPMM_DROPOUT 2
 #define SGS_SPMM_ACCUM 4
+#define SGS_SPMM_ADD_ROOT 8 /* out holds a per-row term that is added BEFORE bias / ReLU / dropout (SAGEConv root weight) */
 int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what,
                  const int32_t* order /* [N+1] from sgs_csr_build, may be NULL */, const float* dis, const float* loopw,
                  const float* h, int64_t N, int64_t D, const float* bias, float* out, int32_t flags,

@@ -77,4 +77,27 @@ class _Unavailable(nn.Module):
         raise NotImplementedError("out of scope for the oracle shim")
 
 
-GATConv = GINConv = SAGEConv = ChebConv = GAT = GIN = _Unavailable
+class SAGEConv(nn.Module):
+    """Pure-torch restatement of PyG 2.3.1 ``SAGEConv(in, out)`` with its defaults (aggr='mean', root_weight=True,
+    bias=True, normalize=False, project=False, flow source->target), as used at /root/reference/model.py:50:
+        out_i = lin_l(mean_{j -> i} x_j) + lin_r(x_i),   mean over an empty neighbourhood = 0.
+    lin_l = Linear(in, out, bias=True), lin_r = Linear(in, out, bias=False); PyG's default Linear initialisers
+    (kaiming_uniform(a=sqrt(5)) weight, uniform(+-1/sqrt(in)) bias) coincide with nn.Linear's, registration order
+    lin_l.weight, lin_l.bias, lin_r.weight.  Same caveat as GCNConv: third-party arithmetic, parity UNPINNED."""
+
+    def __init__(self, in_channels, out_channels, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, edge_index):
+        n = x.size(0)
+        src, dst = edge_index[0], edge_index[1]
+        agg = torch.zeros(n, x.size(1), dtype=x.dtype, device=x.device).index_add(0, dst, x.index_select(0, src))
+        cnt = torch.zeros(n, dtype=x.dtype, device=x.device).index_add(0, dst, torch.ones_like(dst, dtype=x.dtype))
+        agg = agg / cnt.clamp(min=1).unsqueeze(-1)
+        return self.lin_l(agg) + self.lin_r(x)
+
+
+GATConv = GINConv = ChebConv = GAT = GIN = _Unavailable

@@ -64,7 +64,7 @@ SIGNATURES = {
 
 PREC_FP32, PREC_BF16, PREC_FP16, PREC_TF32 = 0, 1, 2, 3
 SAMPLE_TRAIN, SAMPLE_TEST, SAMPLE_RAW = 0, 1, 2
-SPMM_RELU, SPMM_DROPOUT, SPMM_ACCUM = 1, 2, 4
+SPMM_RELU, SPMM_DROPOUT, SPMM_ACCUM, SPMM_ADD_ROOT = 1, 2, 4, 8
 TOPQ_BINS = 2048
 
 _lock = threading.Lock()

@@ -143,6 +143,7 @@ struct SpmmRow {
         for (int t = 0; t < VEC; ++t) {
           v[t] = acc[k][t];
           if (dis) v[t] = fmaf(selfw, hr[c + t], v[t]);
+          if (flags & SGS_SPMM_ADD_ROOT) v[t] += orow[c + t];   // root term (SAGEConv), inside the activation
           if (bias) v[t] += bias[c + t];
           if (flags & SGS_SPMM_RELU) v[t] = fmaxf(v[t], 0.f);
         }

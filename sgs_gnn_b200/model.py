@@ -124,10 +124,43 @@ class EdgeProbMLP(_EdgeProbBase):
         return super().forward(node_features, edge_index, None, use_checkpoint)
 
 
+class SAGEConv(nn.Module):
+    """PyG 2.3.1 SAGEConv(in, out) with its defaults (mean aggregation, root weight, bias on lin_l only).  Parameter
+    names `lin_l.weight`, `lin_l.bias`, `lin_r.weight` and nn.Linear-equivalent initialisers as in PyG."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, edge_index, relu=False, p_drop=0.0, seed=0):
+        g = ops.graph_of(edge_index, x.size(0))
+        return ops.sage_conv(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, g, relu, p_drop, seed)
+
+
+class EdgeProbSAGE(_EdgeProbBase):
+    """model.py:47-89: ONE SAGEConv layer (registered as `gcn1`, so main.py:100's 'gcn' name filter picks it up as
+    the reference does), dropout on its output, then the shared _edge_score."""
+
+    def __init__(self, in_channels, hidden_dim, dropout_prob=0.2):
+        super().__init__()
+        self.gcn1 = SAGEConv(in_channels, hidden_dim)
+        self.fc1 = nn.Linear(2 * hidden_dim, hidden_dim)
+        self.dropout = nn.Dropout(dropout_prob)
+        self.fc2 = nn.Linear(hidden_dim, 1)
+
+    def embed(self, x, graph):
+        """out = dropout(relu(gcn1(x, g)))   (model.py:63/66)"""
+        return self.gcn1(x, graph, relu=True, p_drop=self._drop(), seed=ops.next_seed())
+
+
 def get_edge_mlp(in_channels, hidden_dim, dropout_prob, edge_mlp_type="MLP"):
-    """model.py:135-145 (GSAGE is outside this build's hot path: SURVEY 8f rank 2)."""
+    """model.py:135-145."""
     if edge_mlp_type == "MLP":
         return EdgeProbMLP(in_channels, hidden_dim, dropout_prob)
+    if edge_mlp_type == "GSAGE":
+        return EdgeProbSAGE(in_channels, hidden_dim, dropout_prob)
     if edge_mlp_type == "GCN":
         return EdgeProbGCN(in_channels, hidden_dim, dropout_prob)
     raise NotImplementedError(edge_mlp_type)

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (PREC_BF16, PREC_FP16, PREC_FP32, PREC_TF32, SAMPLE_RAW, SAMPLE_TEST, SAMPLE_TRAIN,
-                   SPMM_ACCUM, SPMM_DROPOUT, SPMM_RELU, check, lib)
+                   SPMM_ACCUM, SPMM_ADD_ROOT, SPMM_DROPOUT, SPMM_RELU, check, lib)
 
 # ------------------------------------------------------------------------------------------
 # configuration
@@ -394,12 +394,13 @@ def gemm_tn(a, b, out=None, static_b=False, precision=None):
     return gemm(a, 1, m, b, 1, n, m, n, k, out=out, precision=PREC_FP32)
 
 
-def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False):
+def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False, add_root=False):
     rowptr, _perm, nbr, order = csr
     n, d = h.shape
     if out is None:
         out = torch.empty(n, d, dtype=torch.float32, device=h.device)
-    flags = (SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0)
+    flags = ((SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0) |
+             (SPMM_ADD_ROOT if add_root else 0))
     with _timed(f"spmm_d{d}"):
         check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(order), _p(norm.dis) if norm is not None else None,
                              _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
@@ -472,6 +473,79 @@ class GCNConvFn(torch.autograd.Function):
 
 def gcn_conv(x, weight, bias, graph, edge_weight=None, relu=False, p_drop=0.0, seed=0):
     return GCNConvFn.apply(x, weight, bias, edge_weight, graph, relu, float(p_drop), int(seed))
+
+
+class SAGEConvFn(torch.autograd.Function):
+    """PyG 2.3.1 SAGEConv defaults (mean aggregation + root weight) with the fused ReLU + dropout epilogue
+    EdgeProbSAGE applies (model.py:50,63,66):   out = dropout(relu(mean_{j->i}(x_j) W_l^T + b_l + x_i W_r^T)).
+    The projections commute with the mean, so both run first on the tcgen05 GEMM (F -> H) and the SpMM (K3b, no
+    self term, edge weight 1/in-degree) gathers H-wide rows and accumulates onto the root term.
+    Backward: the same SpMM over the by-source CSR, dW by the TN GEMM."""
+
+    @staticmethod
+    def _mean_weights(graph):
+        c = getattr(graph, "_mean_w", None)
+        if c is None:
+            rp_d, pm_d, _, _ = graph.csr_dst
+            rp_s, _, nb_s, _ = graph.csr_src
+            indeg = (rp_d[1:] - rp_d[:-1]).clamp(min=1).to(torch.float32)
+            inv = 1.0 / indeg
+            n = graph.num_nodes
+            rows_d = torch.repeat_interleave(torch.arange(n, device=graph.device), (rp_d[1:] - rp_d[:-1]).long(),
+                                             output_size=graph.num_edges)
+            w_dst = inv[rows_d].contiguous()                      # by-destination CSR order: 1 / indeg(row)
+            w_src = inv[nb_s[: graph.num_edges].long()].contiguous()   # by-source CSR order: 1 / indeg(dst of the edge)
+            c = graph._mean_w = (w_dst, w_src)
+        return c
+
+    @staticmethod
+    def forward(ctx, x, w_l, b_l, w_r, graph, relu, p_drop, seed):
+        x = _req(x, torch.float32, "x")
+        if x.size(0) != graph.num_nodes:
+            raise RuntimeError("x must have one row per node")
+        w_dst, _ = SAGEConvFn._mean_weights(graph)
+        static = not x.requires_grad
+        h_l = linear_nt(x, _req(w_l, torch.float32, "lin_l.weight"), static_x=static)
+        out = linear_nt(x, _req(w_r, torch.float32, "lin_r.weight"), static_x=static)   # root term
+        spmm(graph.csr_dst, w_dst, None, h_l, _req(b_l, torch.float32, "lin_l.bias"), relu, p_drop, seed, out=out,
+             add_root=True)
+        ctx.graph, ctx.relu, ctx.p_drop = graph, relu, p_drop
+        ctx.save_for_backward(x, w_l, w_r, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w_l, w_r, out = ctx.saved_tensors
+        graph = ctx.graph
+        n, d = gout.shape
+        gout = _req(gout, torch.float32, "grad")
+        if ctx.relu:
+            g = torch.empty_like(gout)
+            scale = 1.0 / (1.0 - ctx.p_drop) if ctx.p_drop > 0 else 1.0
+            check(lib().sgs_act_bwd(_p(gout), _p(out), gout.numel(), scale, _p(g), _stream()), "sgs_act_bwd")
+        else:
+            g = gout
+        need_x, need_wl, need_bl, need_wr = ctx.needs_input_grad[:4]
+        dx = dwl = dbl = dwr = None
+        if need_bl:
+            dbl = torch.empty(d, dtype=torch.float32, device=g.device)
+            check(lib().sgs_colsum(_p(g), n, d, _p(dbl), _stream()), "sgs_colsum")
+        if need_wr:
+            dwr = gemm_tn(g, x, static_b=not x.requires_grad)
+        if need_wl or need_x:
+            _, w_src = SAGEConvFn._mean_weights(graph)
+            dh = spmm(graph.csr_src, w_src, None, g)
+            if need_wl:
+                dwl = gemm_tn(dh, x, static_b=not x.requires_grad)
+            if need_x:
+                prec = PREC_TF32 if _state["gemm"] != PREC_FP32 else PREC_FP32
+                dx = linear_nt(dh, w_l.t().contiguous(), precision=prec) + linear_nt(g, w_r.t().contiguous(),
+                                                                                     precision=prec)
+        return dx, dwl, dbl, dwr, None, None, None, None
+
+
+def sage_conv(x, w_l, b_l, w_r, graph, relu=False, p_drop=0.0, seed=0):
+    return SAGEConvFn.apply(x, w_l, b_l, w_r, graph, relu, float(p_drop), int(seed))
 
 
 # ------------------------------------------------------------------------------------------

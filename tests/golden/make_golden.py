@@ -8,6 +8,7 @@ What the fixtures pin (SURVEY.md section 8c -- the reference ships no golden vec
   sampler_*.npz   sampling.gumbel_softmax_sampling mask/weights for given (p, prob)
                   with the Exp(1) noise torch.multinomial drew (train and istest).
   scorer_*.npz    model.EdgeProbGCN forward probabilities (eval mode => no dropout).
+  sage_*.npz      model.EdgeProbSAGE forward probabilities + parameter gradients (eval mode).
   gnn_*.npz       model.GNNModel forward logits, weighted and unweighted.
   losses_*.npz    utils.consistency_loss, reg1 BCE block, CE -- values + grads.
   step_*.npz      training_hybrid.train / training_straight_through.train over
@@ -138,6 +139,36 @@ def golden_forward():
         sum_label=float(labels[valid].sum()))
 
 
+def golden_sage():
+    """model.EdgeProbSAGE (model.py:47-89) forward probabilities + parameter gradients, eval-mode dropout, on the full
+    graph and with a random message-passing subgraph; the reference class runs on the shim's SAGEConv."""
+    b = synth.make_graph(None, seed=13, n=350, e=2800, f=20, c=4)
+    h = 32
+    torch.manual_seed(23)
+    model = ref.model.GNNModel(20, h, 4, 0.3, "GSAGE")
+    model.eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert [k for k in sd if k.startswith("edge_prob_mlp.gcn1")] == [
+        "edge_prob_mlp.gcn1.lin_l.weight", "edge_prob_mlp.gcn1.lin_l.bias", "edge_prob_mlp.gcn1.lin_r.weight"]
+    torch.manual_seed(6)
+    ridx = torch.multinomial(torch.softmax(b.prob, -1), 560, replacement=False)
+    rei = b.edge_index[:, ridx]
+    gup = torch.randn(b.edge_index.size(1))
+    out = {}
+    for tag, sub in (("full", None), ("sparse", rei)):
+        model.zero_grad()
+        p = model.edge_prob_mlp(b.x, b.edge_index, sub).squeeze()
+        (p * gup).sum().backward()
+        out["p_" + tag] = p.detach()
+        for k, v in model.edge_prob_mlp.named_parameters():
+            out[f"grad_{tag}.{k}"] = v.grad.clone()
+        with torch.no_grad():
+            o = ox.edge_prob_sage(sd, b.x, b.edge_index, sub, training=False).squeeze()
+        assert torch.allclose(o, p.detach(), atol=1e-6)
+    npz("sage_small.npz", x=b.x, edge_index=b.edge_index, prob=b.prob, rand_edge_index=rei, gup=gup, hidden=h, **out,
+        **{"sd." + k: v for k, v in sd.items()})
+
+
 def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
     b = synth.make_graph(None, seed=seed, n=n, e=e, f=f, c=c, homophily=0.7)
     q = int(e * 0.2)
@@ -200,7 +231,9 @@ def golden_eval():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval"]
+    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval", "sage"]
+    if "sage" in which:
+        golden_sage()
     if "sampler" in which:
         golden_sampler()
     if "forward" in which:

@@ -127,3 +127,42 @@ def test_fused_edge_loss_class_counts_vs_oracle(dev, c, q, n):
     gl, gp = torch.autograd.grad(loss, [logits, p_s])
     assert relerr(gl.cpu().double(), rg[0]) < RTOL
     assert relerr(gp.cpu().double(), rg[1]) < RTOL
+
+
+def test_golden_sage_scorer(dev):
+    """EdgeProbSAGE drop-in (mean-aggregation SpMM + root term inside the fused epilogue) against the fixture produced
+    by the reference's EdgeProbSAGE: probabilities and all parameter gradients."""
+    from sgs_gnn_b200.model import GNNModel
+    z = load_golden("sage_small.npz")
+    sd = {k[3:]: t(v) for k, v in z.items() if k.startswith("sd.")}
+    model = GNNModel(20, int(z["hidden"]), 4, 0.3, "GSAGE")
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    x, ei, rei, gup = t(z["x"], dev), t(z["edge_index"], dev), t(z["rand_edge_index"], dev), t(z["gup"], dev)
+    for tag, sub in (("full", None), ("sparse", rei)):
+        model.zero_grad()
+        p = model.edge_prob_mlp(x, ei, sub).squeeze()
+        assert relerr(p.detach().cpu(), t(z["p_" + tag])) < RTOL
+        (p * gup).sum().backward()
+        for k, v in model.edge_prob_mlp.named_parameters():
+            assert relerr(v.grad.cpu(), t(z[f"grad_{tag}.{k}"])) < 5 * RTOL, (tag, k)
+
+
+def test_hybrid_epoch_with_sage_scorer_trains(dev):
+    """training_hybrid.train end to end with --edge_mlp_type GSAGE (dropout on): finite decreasing loss."""
+    from types import SimpleNamespace
+    import torch.nn as nn
+    from sgs_gnn_b200 import synth, training_hybrid
+    from sgs_gnn_b200.model import GNNModel
+    torch.manual_seed(0)
+    b = synth.make_graph(None, seed=17, n=600, e=7000, f=24, c=4).to(dev)
+    model = GNNModel(24, 64, 4, 0.3, "GSAGE").to(dev)
+    og = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-2)
+    oe = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-2)
+    oa = torch.optim.Adam(model.parameters(), lr=1e-2)
+    args = SimpleNamespace(device=dev, mode="learned", hybrid_checkpoint=False, conditional=False, sparse_edge_mlp=True,
+                           t_init=0.7, t_min=0.5, degree_bias_coef=0.3, reg1=True, reg2=True, regularizer1_coef=1.0,
+                           consist_reg_coef=0.5, pipeline="hybrid")
+    losses = [training_hybrid.train(args, ep, 20, model, og, oe, oa, nn.CrossEntropyLoss(), [b], q=1400,
+                                    alternate_frequency=0)[0] for ep in range(1, 9)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]

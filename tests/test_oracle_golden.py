@@ -127,3 +127,20 @@ def test_degree_prior_is_a_distribution():
     b = synth.make_graph("smallcora", seed=3)
     assert torch.equal(ox.degree_prior(b.edge_index, b.num_nodes), b.prob)
     assert abs(float(b.prob.sum()) - 1.0) < 1e-4
+
+
+def test_sage_scorer_matches_reference():
+    """oracle/extended.edge_prob_sage against the reference's EdgeProbSAGE (model.py:47-89) fixture: probabilities
+    and parameter gradients, full-graph and sparse message passing."""
+    z = load_golden("sage_small.npz")
+    x, ei, rei, gup = t(z["x"]), t(z["edge_index"]), t(z["rand_edge_index"]), t(z["gup"])
+    for tag, sub in (("full", None), ("sparse", rei)):
+        params = {k[3:]: t(v).clone().requires_grad_(k.startswith("sd.edge_prob_mlp.")) for k, v in z.items()
+                  if k.startswith("sd.")}
+        p = ox.edge_prob_sage(params, x, ei, sub, training=False).squeeze()
+        assert torch.allclose(p.detach(), t(z["p_" + tag]), atol=1e-6)
+        (p * gup).sum().backward()
+        for k, v in params.items():
+            if k.startswith("edge_prob_mlp."):
+                want = t(z[f"grad_{tag}.{k[len('edge_prob_mlp.'):]}"])
+                assert torch.allclose(v.grad, want, rtol=1e-4, atol=1e-6), (tag, k)

@@ -73,3 +73,25 @@ def test_oracle_step_with_dropout_uses_same_rng_stream():
     else:
         l2 = torch.nn.functional.cross_entropy(ro[b.train_mask], b.y[b.train_mask])
     assert abs(float(l2) - loss) < 1e-5
+
+
+def test_sage_state_dict_and_forward_live():
+    """EdgeProbSAGE: same state_dict keys / initial values as the reference under the same seed (the 'gcn' name filter
+    of main.py:100 therefore selects the same tensors), and the oracle restatement equals the reference forward."""
+    ref = ref_loader.load()
+    from sgs_gnn_b200.model import GNNModel
+    torch.manual_seed(4)
+    a = ref.model.GNNModel(10, 16, 3, 0.3, "GSAGE")
+    torch.manual_seed(4)
+    b = GNNModel(10, 16, 3, 0.3, "GSAGE")
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert [n for n, _ in a.named_parameters() if "gcn" in n] == [n for n, _ in b.named_parameters() if "gcn" in n]
+    g = synth.make_graph(None, seed=3, n=120, e=900, f=10, c=3)
+    a.eval()
+    with torch.no_grad():
+        want = a.edge_prob_mlp(g.x, g.edge_index, g.edge_index[:, ::5])
+        got = ox.edge_prob_sage(dict(sa), g.x, g.edge_index, g.edge_index[:, ::5], training=False)
+    assert torch.allclose(got, want, atol=1e-6)
