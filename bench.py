@@ -236,8 +236,14 @@ def run_gpu_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    args.pipeline = a.pipeline
+    if a.pipeline == "straight_through":
+        from sgs_gnn_b200 import training_straight_through as train_mod
+    else:
+        train_mod = training_hybrid
+
     def epoch(loader, ep):
-        return training_hybrid.train(args, ep, 1000, model, og, oe, oa, crit, loader, q=q, alternate_frequency=0)
+        return train_mod.train(args, ep, 1000, model, og, oe, oa, crit, loader, q=q, alternate_frequency=0)
 
     # ---- resident arm ----
     loader = [batch]
@@ -394,7 +400,7 @@ def run_gpu_arm(a):
     nnz = q_loc + n
     n_train = int(batch.train_mask.sum())
     alg = {
-        "edge_score_bwd": ("tensor", q_loc * 787968.0),
+        "edge_score_bwd": ("tensor", (q_loc if a.pipeline == "hybrid" else e_k1) * 787968.0),
         "spmm_d256": ("hbm", nnz * (4 * 256 + 8) + n * (4 * 256 + 4)),
         f"spmm_d{c}": ("hbm", nnz * (4 * c + 8) + n * (4 * c + 4)),
         "edge_grad_d256": ("hbm", nnz * (2 * 4 * 256 + 12)),
@@ -431,7 +437,7 @@ def run_gpu_arm(a):
             "config": {"workload": f"{a.workload}-shape hybrid epoch, single full-graph batch" +
                                    ("" if a.scale == 1.0 else f" (scaled {a.scale:g}x)"),
                        "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
-                       "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": "hybrid",
+                       "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": a.pipeline,
                        "conditional": True,
                        "gate": ("forced learned-wins: both forwards + gate are computed, then every step runs the full "
                                 "learned branch incl. the scorer backward" if a.gate == "learned" else "natural"),
@@ -470,6 +476,8 @@ def main():
                     help="N > 1: shard ONE graph by destination range (strong scaling) or one graph per rank (weak)")
     ap.add_argument("--gate", default="learned", choices=["learned", "natural"],
                     help="learned: every step takes the learned-wins branch (full work); natural: the reference's gate")
+    ap.add_argument("--pipeline", default="hybrid", choices=["hybrid", "straight_through"],
+                    help="hybrid (BASELINE.json's metric) or straight_through (dense scorer backward over all E edges)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
