@@ -795,12 +795,12 @@ class EdgeLossState:
 
 
 _FUSED_MAX_CLASSES = 64
-_edge_states = {}   # id(acc tensor) -> EdgeLossState of the forward that produced it (one live entry per step)
 
 
 def edge_state_of(acc):
-    st = _edge_states.get(id(acc))
-    return st[1] if st is not None and st[0]() is acc else None
+    """The EdgeLossState the fused forward attached to its accumulator tensor (None for the two-kernel path).  A
+    caller that re-slices / all-reduces `acc` (sharded step) keeps the state and passes it to fused_loss itself."""
+    return getattr(acc, "_sgs_edge_state", None)
 
 
 def loss_forward(logits, y, train_mask_u8, sub=None, p_s=None, row_mask_u8=None):
@@ -819,9 +819,7 @@ def loss_forward(logits, y, train_mask_u8, sub=None, p_s=None, row_mask_u8=None)
             check(lib().sgs_loss_fwd_fused(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(row_mask_u8), _p(sub.src),
                                            _p(sub.dst), _p(p_s), q, _p(acc), _p(dlog_e), _p(u1), _p(u2), _p(code),
                                            _stream()), "sgs_loss_fwd_fused")
-        import weakref
-        _edge_states.clear()
-        _edge_states[id(acc)] = (weakref.ref(acc), EdgeLossState(dlog_e, u1, u2, q))
+        acc._sgs_edge_state = EdgeLossState(dlog_e, u1, u2, q)
         return acc
     check(lib().sgs_loss_fwd(_p(logits), n, c, _p(y), _p(train_mask_u8), _p(row_mask_u8),
                              _p(sub.src) if with_edges else None,
