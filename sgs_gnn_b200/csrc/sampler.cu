@@ -4,6 +4,8 @@
 //   ballot/scan compaction in ascending edge id.  HBM-bound: 128-bit streaming loads throughout.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace sgs {
 
 constexpr int kBins = SGS_TOPQ_BINS;  // 2048
@@ -85,15 +87,17 @@ topq_keys_kernel(const float* __restrict__ p, const float* __restrict__ prob, co
   if (bad) state[5] = 1;
 }
 
+// gate (may be NULL): the kernel runs only if *gate != 0 (fallback passes of the sampled-window fast path)
 __global__ void __launch_bounds__(512)
 topq_hist_kernel(const uint32_t* __restrict__ keys, int64_t E, unsigned long long* __restrict__ hist,
-                 const long long* __restrict__ state, int level) {
+                 const long long* __restrict__ state, int level, const uint32_t* __restrict__ gate) {
   __shared__ int sh[kBins];
+  if (gate && *gate == 0) return;
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const int shift = level_shift(level);
-  const int hi_shift = (level == 1) ? 20 : 9;  // bits above this digit that must match the prefix
-  const uint32_t prefix_hi = (uint32_t)state[0] >> hi_shift;
+  const int hi_shift = (level == 0) ? 31 : ((level == 1) ? 20 : 9);  // bits above this digit must match the prefix
+  const uint32_t prefix_hi = (level == 0) ? 0u : ((uint32_t)state[0] >> hi_shift);
   const uint32_t mask = (uint32_t)level_bins(level) - 1;
   const int64_t n4 = E >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,9 +127,10 @@ topq_hist_kernel(const uint32_t* __restrict__ keys, int64_t E, unsigned long lon
 // (the bin b >= 1, scanning down from the top, with  #keys above b < k <= #keys above b + hist[b];  bin 0 if none).
 __global__ void __launch_bounds__(1024)
 topq_find_kernel(unsigned long long* __restrict__ hist, long long* __restrict__ state, long long k_total,
-                 int level) {
+                 int level, const uint32_t* __restrict__ gate) {
   __shared__ long long warp_tot[32];
   __shared__ long long s_bin, s_rem, s_cnt;
+  if (gate && *gate == 0) return;
   const int nb = level_bins(level);
   const int per = nb >= 1024 ? nb / 1024 : 1;          // bins per thread (2 or 1)
   const int b0 = threadIdx.x * per;
@@ -180,6 +185,193 @@ topq_find_kernel(unsigned long long* __restrict__ hist, long long* __restrict__ 
   }
   __syncthreads();   // every thread has read its bins
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0ull;
+}
+
+// ---------------------------------------------------------------------------------------
+// Sampled-window fast path of the first two radix levels (single-GPU sgs_sample_topq, large E).
+// A full level-0 histogram costs one MATCH.ANY (or one shared-memory atomic) per key: ncu r01 shows the keys pass
+// bound by the ADU pipe at 91 % with DRAM at 24-30 %.  Instead:
+//   (1) a 1/64 strided sample of the keys is histogrammed and the level-0 bin holding the q-th largest key is
+//       PREDICTED (window = that bin and its two neighbours),
+//   (2) the full keys pass only counts the keys above the window (one compare per key, per-thread counters) and
+//       histograms the 22-bit prefix (level-0 bin, level-1 digit) of the ~15 % of keys inside the window with plain
+//       shared-memory atomics,
+//   (3) the exact counts decide: if the q-th largest key lies inside the window the 22-bit prefix is read off the
+//       window histogram (levels 0 and 1 done, bit-exact by construction); otherwise a device flag enables the
+//       classic level-0 / level-1 passes over the stored keys (they are launched either way and exit on the flag).
+// ---------------------------------------------------------------------------------------
+constexpr int kWinBins = 3;                                    // level-0 bins in the window
+constexpr int kWinHist = kWinBins * kBins;                     // 6144 (window bin, level-1 digit) counters
+constexpr size_t kWinScratchBytes = (size_t)(kBins + kWinHist + 16) * sizeof(unsigned long long);
+// scratch layout (unsigned long long): shist[kBins] | whist[kWinHist] | misc[16]: 0 = window low bin, 1 = miss flag
+// (also read as uint32 gate), 2 = #keys above the window, 3 = #sampled keys
+
+__global__ void __launch_bounds__(256)
+topq_sample_kernel(const float* __restrict__ p, const float* __restrict__ prob, const float* __restrict__ noise,
+                   int64_t E, float c_p, float c_prob, int mode, const float* __restrict__ S, int stride,
+                   unsigned long long* __restrict__ shist, unsigned long long* __restrict__ misc) {
+  __shared__ int sh[kBins];
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const float S_eff = (mode == SGS_SAMPLE_RAW) ? 1.f : __fadd_rn(S[0], 1e-12f);
+  const bool use_prob = (mode == SGS_SAMPLE_TRAIN);
+  const int64_t n4 = E >> 2;
+  const int64_t ns = (n4 + stride - 1) / stride;               // sampled float4 groups
+  bool bad = false;
+  int cnt = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t * stride;
+    const float4 a = reinterpret_cast<const float4*>(p)[i];
+    const float4 z = reinterpret_cast<const float4*>(noise)[i];
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_prob) b = reinterpret_cast<const float4*>(prob)[i];
+    atomicAdd(&sh[make_key(a.x, b.x, z.x, S_eff, c_p, c_prob, mode, bad) >> 20], 1);
+    atomicAdd(&sh[make_key(a.y, b.y, z.y, S_eff, c_p, c_prob, mode, bad) >> 20], 1);
+    atomicAdd(&sh[make_key(a.z, b.z, z.z, S_eff, c_p, c_prob, mode, bad) >> 20], 1);
+    atomicAdd(&sh[make_key(a.w, b.w, z.w, S_eff, c_p, c_prob, mode, bad) >> 20], 1);
+    cnt += 4;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x)
+    if (sh[i]) atomicAdd(shist + i, (unsigned long long)sh[i]);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(misc + 3, (unsigned long long)cnt);
+}
+
+// one block of 1024 threads: window low bin from the sample histogram (force_miss: a window that cannot hold tau)
+__global__ void __launch_bounds__(1024)
+topq_predict_kernel(const unsigned long long* __restrict__ shist, unsigned long long* __restrict__ misc,
+                    long long k_total, long long E, int force_miss) {
+  __shared__ long long warp_tot[32];
+  __shared__ int s_bin;
+  const int b0 = threadIdx.x * 2;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long c0 = (long long)shist[b0], c1 = (long long)shist[b0 + 1];
+  const long long ns = (long long)misc[3];
+  // rank of the threshold inside the sample (rounded to nearest, at least 1)
+  long long ks = (long long)((double)k_total * (double)ns / (double)E + 0.5);
+  if (ks < 1) ks = 1;
+  if (threadIdx.x == 0) s_bin = 0;
+  long long v = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  if (lane == 0) warp_tot[wid] = v;
+  __syncthreads();
+  long long above = v - (c0 + c1);
+  for (int w = wid + 1; w < 32; ++w) above += warp_tot[w];
+  if (above + c1 < ks && above + c1 + c0 >= ks) s_bin = b0;   // unique (suffix sums are monotone)
+  if (above < ks && above + c1 >= ks) s_bin = b0 + 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int lo = s_bin - 1;
+    if (lo < 0) lo = 0;
+    if (lo > kBins - kWinBins) lo = kBins - kWinBins;
+    if (force_miss) lo = 0;        // keys of valid inputs never reach the three lowest exponent bins' neighbourhood
+    misc[0] = (unsigned long long)lo;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+topq_keys_window_kernel(const float* __restrict__ p, const float* __restrict__ prob, const float* __restrict__ noise,
+                        int64_t E, float c_p, float c_prob, int mode, const float* __restrict__ S,
+                        uint32_t* __restrict__ keys, unsigned long long* __restrict__ whist,
+                        unsigned long long* __restrict__ misc, long long* __restrict__ state) {
+  __shared__ int sh[kWinHist];
+  for (int i = threadIdx.x; i < kWinHist; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const float S_eff = (mode == SGS_SAMPLE_RAW) ? 1.f : __fadd_rn(S[0], 1e-12f);
+  const uint32_t lo = (uint32_t)misc[0];
+  bool bad = false;
+  int above = 0;
+  const int64_t n4 = E >> 2;
+  const bool use_prob = (mode == SGS_SAMPLE_TRAIN);
+  auto classify = [&](uint32_t k) {
+    const uint32_t w = (k >> 20) - lo;            // window bin (unsigned: bins below the window wrap to huge values)
+    above += (int)(w >= (uint32_t)kWinBins && (k >> 20) > lo);
+    if (w < (uint32_t)kWinBins) atomicAdd(&sh[w * kBins + ((k >> 9) & (kBins - 1))], 1);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(p) + i);
+    const float4 z = ld_stream_f4(reinterpret_cast<const float4*>(noise) + i);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_prob) b = ld_stream_f4(reinterpret_cast<const float4*>(prob) + i);
+    uint4 k;
+    k.x = make_key(a.x, b.x, z.x, S_eff, c_p, c_prob, mode, bad);
+    k.y = make_key(a.y, b.y, z.y, S_eff, c_p, c_prob, mode, bad);
+    k.z = make_key(a.z, b.z, z.z, S_eff, c_p, c_prob, mode, bad);
+    k.w = make_key(a.w, b.w, z.w, S_eff, c_p, c_prob, mode, bad);
+    reinterpret_cast<uint4*>(keys)[i] = k;
+    classify(k.x);
+    classify(k.y);
+    classify(k.z);
+    classify(k.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4) {      // tail (E % 4 elements)
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    if (i < E) {
+      const uint32_t k = make_key(p[i], use_prob ? prob[i] : 0.f, noise[i], S_eff, c_p, c_prob, mode, bad);
+      keys[i] = k;
+      classify(k);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kWinHist; i += blockDim.x)
+    if (sh[i]) atomicAdd(whist + i, (unsigned long long)sh[i]);
+  above = warp_sum(above);
+  if ((threadIdx.x & 31) == 0 && above) atomicAdd(misc + 2, (unsigned long long)above);
+  if (bad) state[5] = 1;
+}
+
+// one block of 1024 threads, 6 window counters per thread: either the 22-bit prefix (levels 0 and 1 done) or the
+// miss flag that enables the classic passes
+__global__ void __launch_bounds__(1024)
+topq_find_window_kernel(const unsigned long long* __restrict__ whist, unsigned long long* __restrict__ misc,
+                        long long* __restrict__ state, long long k_total) {
+  constexpr int PER = kWinHist / 1024;
+  __shared__ long long warp_tot[32];
+  __shared__ long long s_idx, s_rem;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b0 = threadIdx.x * PER;
+  long long c[PER], tsum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    c[j] = (long long)whist[b0 + j];
+    tsum += c[j];
+  }
+  if (threadIdx.x == 0) s_idx = -1;
+  long long v = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  if (lane == 0) warp_tot[wid] = v;
+  __syncthreads();
+  long long above = v - tsum;
+  for (int w = wid + 1; w < 32; ++w) above += warp_tot[w];
+  const long long k = k_total - (long long)misc[2];     // rank inside the window (from the top)
+  long long cum = above;
+#pragma unroll
+  for (int j = PER - 1; j >= 0; --j) {
+    if (k >= 1 && cum < k && cum + c[j] >= k) {
+      s_idx = b0 + j;
+      s_rem = k - cum;
+    }
+    cum += c[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_idx < 0) {
+      misc[1] = 1ull;                                   // miss: tau is not inside the window
+    } else {
+      const long long lo = (long long)misc[0];
+      state[0] = ((lo + s_idx / kBins) << 20) | ((s_idx % kBins) << 9);
+      state[1] = s_rem;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -526,7 +718,8 @@ int32_t sgs_topq_keys(const float* p, const float* prob, const float* noise, int
 
 int32_t sgs_topq_find(int64_t* hist, int64_t* state, int64_t k_total, int32_t level, sgs_stream_t stream) {
   SGS_CHECK_ARG(hist && state && level >= 0 && level <= 2 && k_total >= 1, "bad arguments");
-  topq_find_kernel<<<1, 1024, 0, as_stream(stream)>>>((unsigned long long*)hist, (long long*)state, k_total, level);
+  topq_find_kernel<<<1, 1024, 0, as_stream(stream)>>>((unsigned long long*)hist, (long long*)state, k_total, level,
+                                                        nullptr);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }
@@ -535,15 +728,16 @@ int32_t sgs_topq_hist(const uint32_t* keys, int64_t E, int64_t* hist, const int6
                       sgs_stream_t stream) {
   SGS_CHECK_ARG(keys && hist && state && (level == 1 || level == 2) && E > 0, "bad arguments");
   topq_hist_kernel<<<stream_grid(E / 4 + 1, 512, 4), 512, 0, as_stream(stream)>>>(
-      keys, E, (unsigned long long*)hist, (const long long*)state, level);
+      keys, E, (unsigned long long*)hist, (const long long*)state, level, nullptr);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }
 
-size_t sgs_topq_workspace_bytes(int64_t E) {
+static size_t compact_bytes(int64_t E) {
   const int64_t nb = ceil_div(E > 0 ? E : 1, kChunk);
-  return (size_t)(2 * nb * sizeof(int32_t) + 256);
+  return (size_t)((2 * nb * sizeof(int32_t) + 255) & ~(size_t)255) + 256;
 }
+size_t sgs_topq_workspace_bytes(int64_t E) { return compact_bytes(E) + kWinScratchBytes; }
 
 int32_t sgs_topq_compact(const uint32_t* keys, int64_t E, const int64_t* state, int64_t tie_skip, int32_t* sel,
                          int64_t q_cap, uint8_t* mask, int64_t* n_sel_out, void* ws, size_t ws_bytes,
@@ -574,10 +768,55 @@ int32_t sgs_sample_topq(const float* p, const float* prob, const float* noise, i
   void* ws2 = (char*)ws + kBins * sizeof(int64_t);
   size_t ws2_bytes = ws_bytes - kBins * sizeof(int64_t);
   int32_t rc;
-  if ((rc = sgs_topq_keys(p, prob, noise, E, one_minus_coef, coef, mode, S, keys, hist, state, stream))) return rc;
-  if ((rc = sgs_topq_find(hist, state, q, 0, stream))) return rc;
-  if ((rc = sgs_topq_hist(keys, E, hist, state, 1, stream))) return rc;
-  if ((rc = sgs_topq_find(hist, state, q, 1, stream))) return rc;
+  // debug / test knobs (read on every call): SGS_TOPQ_FAST_MIN_E moves the size threshold of the fast path,
+  // SGS_TOPQ_FORCE_MISS=1 makes the predicted window miss so that the fallback passes run
+  const char* env_min = getenv("SGS_TOPQ_FAST_MIN_E");
+  const int64_t fast_min_e = env_min ? (int64_t)atoll(env_min) : (int64_t)1 << 20;
+  if (E >= fast_min_e && E >= 4096) {
+    // ---- sampled-window fast path (see above); scratch = the tail of the workspace ----
+    SGS_CHECK_ARG(p && noise && keys && state, "null pointer");
+    SGS_CHECK_ARG(mode == SGS_SAMPLE_RAW || S, "S required");
+    SGS_CHECK_ARG(mode != SGS_SAMPLE_TRAIN || prob, "prob required in train mode");
+    SGS_CHECK_ARG((((uintptr_t)p | (uintptr_t)noise | (uintptr_t)keys | (uintptr_t)prob) & 15) == 0,
+                  "p/prob/noise/keys must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    unsigned long long* shist = (unsigned long long*)((char*)ws2 + compact_bytes(E));
+    unsigned long long* whist = shist + kBins;
+    unsigned long long* misc = whist + kWinHist;
+    const uint32_t* gate = (const uint32_t*)(misc + 1);
+    const char* env_miss = getenv("SGS_TOPQ_FORCE_MISS");
+    const int force_miss = env_miss ? atoi(env_miss) : 0;
+    SGS_CUDA(cudaMemsetAsync(hist, 0, kBins * sizeof(int64_t), st));
+    SGS_CUDA(cudaMemsetAsync(state, 0, 8 * sizeof(int64_t), st));
+    SGS_CUDA(cudaMemsetAsync(shist, 0, kWinScratchBytes, st));
+    const int stride = 64;
+    topq_sample_kernel<<<stream_grid(E / 4 / stride + 1, 256, 4), 256, 0, st>>>(p, prob, noise, E, one_minus_coef,
+                                                                                coef, mode, S, stride, shist, misc);
+    SGS_LAUNCH_CHECK();
+    topq_predict_kernel<<<1, 1024, 0, st>>>(shist, misc, q, E, force_miss);
+    SGS_LAUNCH_CHECK();
+    topq_keys_window_kernel<<<stream_grid(E / 4 + 1, 512, 4), 512, 0, st>>>(p, prob, noise, E, one_minus_coef, coef,
+                                                                            mode, S, keys, whist, misc,
+                                                                            (long long*)state);
+    SGS_LAUNCH_CHECK();
+    topq_find_window_kernel<<<1, 1024, 0, st>>>(whist, misc, (long long*)state, q);
+    SGS_LAUNCH_CHECK();
+    // classic level-0 / level-1 passes over the stored keys: exit immediately unless the window missed tau
+    const int hg = stream_grid(E / 4 + 1, 512, 4);
+    topq_hist_kernel<<<hg, 512, 0, st>>>(keys, E, (unsigned long long*)hist, (const long long*)state, 0, gate);
+    SGS_LAUNCH_CHECK();
+    topq_find_kernel<<<1, 1024, 0, st>>>((unsigned long long*)hist, (long long*)state, q, 0, gate);
+    SGS_LAUNCH_CHECK();
+    topq_hist_kernel<<<hg, 512, 0, st>>>(keys, E, (unsigned long long*)hist, (const long long*)state, 1, gate);
+    SGS_LAUNCH_CHECK();
+    topq_find_kernel<<<1, 1024, 0, st>>>((unsigned long long*)hist, (long long*)state, q, 1, gate);
+    SGS_LAUNCH_CHECK();
+  } else {
+    if ((rc = sgs_topq_keys(p, prob, noise, E, one_minus_coef, coef, mode, S, keys, hist, state, stream))) return rc;
+    if ((rc = sgs_topq_find(hist, state, q, 0, stream))) return rc;
+    if ((rc = sgs_topq_hist(keys, E, hist, state, 1, stream))) return rc;
+    if ((rc = sgs_topq_find(hist, state, q, 1, stream))) return rc;
+  }
   if ((rc = sgs_topq_hist(keys, E, hist, state, 2, stream))) return rc;
   if ((rc = sgs_topq_find(hist, state, q, 2, stream))) return rc;
   return sgs_topq_compact(keys, E, state, 0, sel, q, mask, (int64_t*)state + 7, ws2, ws2_bytes, stream);

@@ -167,3 +167,36 @@ def test_sharded_select_steps_equal_single_select(dev, ties):
         sels.append(sel.long() + a)
     got = torch.cat(sels)
     assert torch.equal(got, single.sel.long())
+
+
+@pytest.mark.parametrize("path", ["window", "forced_miss", "classic"])
+@pytest.mark.parametrize("e,q,mode", [(4099, 811, "train"), (100003, 20000, "train"), (2_500_003, 500_000, "train"),
+                                      (2_500_003, 1, "test"), (1_300_000, 1_299_999, "raw")])
+def test_sampled_window_path_is_bit_exact(dev, monkeypatch, path, e, q, mode):
+    """The sampled-window fast path of the first two radix levels (sgs_sample_topq, E >= 2^20 by default), its
+    fallback when the predicted window misses tau, and the classic full-histogram path must all give the oracle's
+    selection bit for bit (every count that decides tau is exact in all three)."""
+    from sgs_gnn_b200 import ops
+    if path == "classic":
+        monkeypatch.setenv("SGS_TOPQ_FAST_MIN_E", str(1 << 40))
+    else:
+        monkeypatch.setenv("SGS_TOPQ_FAST_MIN_E", "4096")
+        if path == "forced_miss":
+            monkeypatch.setenv("SGS_TOPQ_FORCE_MISS", "1")
+    g = torch.Generator().manual_seed(e + q)
+    p = torch.rand(e, generator=g) ** 3           # skewed scores: several exponent bins are populated
+    prob = torch.softmax(torch.rand(e, generator=g) * 4, 0)
+    noise = ox.exponential_noise(e, g)
+    if mode == "raw":
+        keys = p / noise
+        sel_want = ox.topq_select(keys, q)[0]
+        r = ops.sample_topq(p.to(dev), None, q, ops.SAMPLE_RAW, 0.0, noise=noise.to(dev), want_mask=True)
+        assert torch.equal(r.sel.cpu().long(), sel_want)
+        return
+    S = p.sum().reshape(1)
+    want = ox.sample_topq(p, prob, q, noise, 0.3, mode == "test", S=S[0])
+    r = ops.sample_topq(p.to(dev), prob.to(dev), q, ops.SAMPLE_TEST if mode == "test" else ops.SAMPLE_TRAIN, 0.3,
+                        noise=noise.to(dev), S=S.to(dev), want_mask=True)
+    assert torch.equal(r.sel.cpu().long(), want.sel)
+    assert torch.equal(r.mask.view(torch.bool).cpu(), want.mask)
+    assert abs(r.tau - want.tau) == 0.0
