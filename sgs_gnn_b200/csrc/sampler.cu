@@ -498,19 +498,38 @@ topq_write_kernel(const uint32_t* __restrict__ keys, int64_t E, const long long*
   long long g_before = (long long)blk_gt[blockIdx.x] + wg[wid] + (ig - gt);
   long long e_before = (long long)blk_eq[blockIdx.x] + we[wid] + (ie - eq);
   uint64_t mbits = 0;
+  if (eq == 0) {
+    // fast path (no threshold tie among this thread's keys -- ties are a handful per 10^8 keys): the output
+    // position advances by one per selected key; 32-bit arithmetic on a per-thread base pointer
+    const long long pos0 = g_before + (e_before < avail ? e_before : avail);
+    long long room = q_cap - pos0;
+    int lim = sel ? (room > 8 ? 8 : (room < 0 ? 0 : (int)room)) : 0;
+    int32_t* out = sel ? sel + pos0 : nullptr;
+    int n_out = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const bool in = base + j < E;
-    const bool is_gt = in && (k[j] > tau);
-    const bool is_eq = in && (k[j] == tau);
-    const bool take = is_gt || (is_eq && e_before < avail);
-    if (take) {
-      const long long pos = g_before + (e_before < avail ? e_before : avail);
-      if (sel && pos < q_cap) sel[pos] = (int32_t)(base + j);
-      mbits |= (uint64_t)1 << (8 * j);
+    for (int j = 0; j < 8; ++j) {
+      if (base + j < E && k[j] > tau) {
+        if (n_out < lim) out[n_out] = (int32_t)(base + j);
+        ++n_out;
+        mbits |= (uint64_t)1 << (8 * j);
+      }
     }
-    g_before += is_gt;
-    e_before += is_eq;
+    g_before += gt;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = base + j < E;
+      const bool is_gt = in && (k[j] > tau);
+      const bool is_eq = in && (k[j] == tau);
+      const bool take = is_gt || (is_eq && e_before < avail);
+      if (take) {
+        const long long pos = g_before + (e_before < avail ? e_before : avail);
+        if (sel && pos < q_cap) sel[pos] = (int32_t)(base + j);
+        mbits |= (uint64_t)1 << (8 * j);
+      }
+      g_before += is_gt;
+      e_before += is_eq;
+    }
   }
   if (mask) {
     if (base + 8 <= E && ((uintptr_t)(mask + base) & 7) == 0) {
