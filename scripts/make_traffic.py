@@ -34,8 +34,10 @@ def main(hot, spmm, dst):
     put("edge_score_bwd", "edge_score_tc2_kernel<__half,1> + edge_score_bwd_df_kernel + edge_score_bwd_dw_kernel",
         (sum(p[0] for p in parts), sum(p[1] for p in parts)))
     put("loss_fwd", "loss_edges_fused_kernel<3>", mean(h, lambda k: "loss_edges_fused" in k))
-    kk, ww = mean(h, lambda k: "topq_keys" in k), mean(h, lambda k: "topq_write" in k)
-    put("sample_topq", "topq_keys + topq_write (hist/find/count/scan: < 0.1 GB)", (kk[0] + ww[0], kk[1] + ww[1]))
+    tq = [(a, b) for k, a, b in h if "topq_" in k]
+    ndraw = max(1, sum(1 for k, _, _ in h if "topq_write" in k))
+    put("sample_topq", "all topq_* kernels of one draw (sample, predict, keys_window, find_window, hist, find, count, "
+        "scan, write)", (sum(a for a, _ in tq) / ndraw, sum(b for _, b in tq) / ndraw))
     put("spmm_d256", "spmm_kernel<4,2>", mean(s, lambda k: "spmm_kernel<4, 2>" in k))
     put("spmm_d41", "spmm_kernel<1,2>", mean(s, lambda k: "spmm_kernel<1, 2>" in k))
     put("edge_grad_d256", "edge_grad_sddmm_kernel<4,2>", mean(s, lambda k: "sddmm_kernel<4, 2>" in k))
