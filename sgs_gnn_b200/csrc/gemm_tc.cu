@@ -137,17 +137,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           const uint32_t a_addr = sm_addr + slot * STAGE_BYTES;
           const uint32_t b_addr = a_addr + BM * BK * 4;
-#ifdef SGS_DEBUG_TN
-          if (TN && blockIdx.x == 0 && it == 0) {
-            const float* fa = reinterpret_cast<const float*>(sm + slot * STAGE_BYTES);
-            const float* fb = fa + BM * BK;
-            float sa = 0.f, sb = 0.f;
-            for (int q = 0; q < BM * BK; ++q) { sa += fabsf(fa[q]); sb += fabsf(fb[q]); }
-            printf("TN dbg: sum|A stage|=%f sum|B stage|=%f A[0..3]=%f %f %f %f idesc=%08x\n", sa, sb, fa[0], fa[1], fa[2], fa[3], idesc);
-            for (int q = 0; q < BM * BK; ++q) if (fa[q] != 0.f) printf("  A nz at float %d = %f\n", q, fa[q]);
-            for (int q = 0; q < BN * BK; ++q) if (fb[q] != 0.f) printf("  B nz at float %d = %f\n", q, fb[q]);
-          }
-#endif
 #pragma unroll
           for (int k8 = 0; k8 < BK / 8; ++k8) {
             if (TN)   // K = 8 rows = two 4-row swizzle groups per MMA; 32-float blocks along M / N are BK*128 B apart
