@@ -176,6 +176,11 @@ def run_reference_arm(a):
     if rank != 0:
         return
     scale = a.cpu_scale
+    # torchrun exports OMP_NUM_THREADS=1 per rank; the reference arm is one process using every host core it can
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     r = cpu_epochs(a.workload, scale, a.steps, a.warmup)
     line = {"impl": "reference", "metric": "sampled_edges_per_s", "value": r["value"], "unit": "edges/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
@@ -426,7 +431,7 @@ def run_gpu_arm(a):
         kernels.append(ent)
 
     cpu = None
-    if not a.no_cpu:
+    if not a.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only (rank 0 is the only rank there)
         cpu = cpu_epochs(a.workload, a.cpu_scale, 2, 1, a.drop_rate)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
