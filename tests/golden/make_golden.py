@@ -9,6 +9,7 @@ What the fixtures pin (SURVEY.md section 8c -- the reference ships no golden vec
                   with the Exp(1) noise torch.multinomial drew (train and istest).
   scorer_*.npz    model.EdgeProbGCN forward probabilities (eval mode => no dropout).
   sage_*.npz      model.EdgeProbSAGE forward probabilities + parameter gradients (eval mode).
+  mlp_*.npz       model.EdgeProbMLP forward probabilities + parameter gradients (eval mode).
   gnn_*.npz       model.GNNModel forward logits, weighted and unweighted.
   losses_*.npz    utils.consistency_loss, reg1 BCE block, CE -- values + grads.
   step_*.npz      training_hybrid.train / training_straight_through.train over
@@ -169,6 +170,28 @@ def golden_sage():
         **{"sd." + k: v for k, v in sd.items()})
 
 
+def golden_mlp():
+    """model.EdgeProbMLP (model.py:8-45) with random_sampled_edge_index=None (the only shape-consistent form, SURVEY
+    a3): forward probabilities + parameter gradients, eval-mode dropout."""
+    b = synth.make_graph(None, seed=14, n=330, e=2600, f=18, c=4)
+    h = 32
+    torch.manual_seed(24)
+    model = ref.model.GNNModel(18, h, 4, 0.3, "MLP")
+    model.eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    gup = torch.randn(b.edge_index.size(1))
+    p = model.edge_prob_mlp(b.x, b.edge_index, None).squeeze()
+    (p * gup).sum().backward()
+    out = {"p_full": p.detach()}
+    for k, v in model.edge_prob_mlp.named_parameters():
+        out[f"grad.{k}"] = v.grad.clone()
+    with torch.no_grad():
+        o = ox.edge_prob_mlp(sd, b.x, b.edge_index, training=False).squeeze()
+    assert torch.allclose(o, p.detach(), atol=1e-6)
+    npz("mlp_small.npz", x=b.x, edge_index=b.edge_index, gup=gup, hidden=h, **out,
+        **{"sd." + k: v for k, v in sd.items()})
+
+
 def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
     b = synth.make_graph(None, seed=seed, n=n, e=e, f=f, c=c, homophily=0.7)
     q = int(e * 0.2)
@@ -231,7 +254,9 @@ def golden_eval():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval", "sage"]
+    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval", "sage", "mlp"]
+    if "mlp" in which:
+        golden_mlp()
     if "sage" in which:
         golden_sage()
     if "sampler" in which:

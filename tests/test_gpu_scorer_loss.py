@@ -166,3 +166,23 @@ def test_hybrid_epoch_with_sage_scorer_trains(dev):
     losses = [training_hybrid.train(args, ep, 20, model, og, oe, oa, nn.CrossEntropyLoss(), [b], q=1400,
                                     alternate_frequency=0)[0] for ep in range(1, 9)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_golden_mlp_scorer(dev):
+    """EdgeProbMLP drop-in (per-node relu(fcdim(X)) then the fused edge scorer; identical to the reference's per-edge
+    projection whenever dropout is off) against the fixture produced by the reference class; the
+    random_sampled_edge_index form, whose [q] output the reference itself cannot consume, raises."""
+    from sgs_gnn_b200.model import GNNModel
+    z = load_golden("mlp_small.npz")
+    sd = {k[3:]: t(v) for k, v in z.items() if k.startswith("sd.")}
+    model = GNNModel(18, int(z["hidden"]), 4, 0.3, "MLP")
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    x, ei, gup = t(z["x"], dev), t(z["edge_index"], dev), t(z["gup"], dev)
+    p = model.edge_prob_mlp(x, ei, None).squeeze()
+    assert relerr(p.detach().cpu(), t(z["p_full"])) < RTOL
+    (p * gup).sum().backward()
+    for k, v in model.edge_prob_mlp.named_parameters():
+        assert relerr(v.grad.cpu(), t(z[f"grad.{k}"])) < 5 * RTOL, k
+    with pytest.raises(RuntimeError):
+        model.edge_prob_mlp(x, ei, ei[:, :10])

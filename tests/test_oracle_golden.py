@@ -144,3 +144,17 @@ def test_sage_scorer_matches_reference():
             if k.startswith("edge_prob_mlp."):
                 want = t(z[f"grad_{tag}.{k[len('edge_prob_mlp.'):]}"])
                 assert torch.allclose(v.grad, want, rtol=1e-4, atol=1e-6), (tag, k)
+
+
+def test_mlp_scorer_matches_reference():
+    """oracle/extended.edge_prob_mlp against the reference's EdgeProbMLP (model.py:8-45) fixture."""
+    z = load_golden("mlp_small.npz")
+    x, ei, gup = t(z["x"]), t(z["edge_index"]), t(z["gup"])
+    params = {k[3:]: t(v).clone().requires_grad_(k.startswith("sd.edge_prob_mlp.")) for k, v in z.items()
+              if k.startswith("sd.")}
+    p = ox.edge_prob_mlp(params, x, ei, training=False).squeeze()
+    assert torch.allclose(p.detach(), t(z["p_full"]), atol=1e-6)
+    (p * gup).sum().backward()
+    for k, v in params.items():
+        if k.startswith("edge_prob_mlp."):
+            assert torch.allclose(v.grad, t(z[f"grad.{k[len('edge_prob_mlp.'):]}"]), rtol=1e-4, atol=1e-6), k
