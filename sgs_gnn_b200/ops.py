@@ -200,6 +200,7 @@ class Graph:
         self._csr_dst = None
         self._csr_src = None
         self._src_sorted = None   # is `src` non-decreasing?  (None: not checked yet)
+        self._mean_w = None       # SAGEConv mean-aggregation weights in both CSR orders (lazily built)
         self._norm_unw = None
         self._norm_w = None  # (weakref to weight tensor, version, GcnNorm)
 
@@ -484,7 +485,7 @@ class SAGEConvFn(torch.autograd.Function):
 
     @staticmethod
     def _mean_weights(graph):
-        c = getattr(graph, "_mean_w", None)
+        c = graph._mean_w
         if c is None:
             rp_d, pm_d, _, _ = graph.csr_dst
             rp_s, _, nb_s, _ = graph.csr_src
