@@ -134,17 +134,22 @@ def build_model(f, c, device, drop_rate):
 # CPU arm: the oracle on a bounded sample of the same workload
 # ------------------------------------------------------------------------------------------
 
-def cpu_epochs(workload, scale, steps, warmup, drop_rate=0.3):
-    from oracle import extended as ox
+def _cpu_sample(workload, scale):
     from sgs_gnn_b200 import synth
-    torch.manual_seed(42)
     n0, e0 = synth.SHAPES[workload][:2]
     e_s = max(8, round(e0 * scale))
     # keep the sample a simple graph: N shrinks with E but never below ~8*sqrt(E)
     n_s = max(round(n0 * scale), int(8 * e_s ** 0.5) + 1)
-    b = synth.make_graph(workload, seed=42, n=n_s, e=e_s, device="cpu")
+    return synth.make_graph(workload, seed=42, n=n_s, e=e_s, device="cpu")
+
+
+def cpu_epochs(workload, scale, steps, warmup, drop_rate=0.3, sample_perc=SAMPLE_PERC):
+    """CPU oracle PORT (oracle/extended.learned_step + Adam) on a bounded sample of the workload."""
+    from oracle import extended as ox
+    torch.manual_seed(42)
+    b = _cpu_sample(workload, scale)
     e = b.num_edges
-    q = int(e * SAMPLE_PERC)
+    q = int(e * sample_perc)
     f, c = b.x.size(1), b.num_classes
     params = {k: v.requires_grad_(True) for k, v in ox.init_params(f, HIDDEN, c).items()}
     og = torch.optim.Adam([p for n, p in params.items() if "gcn" in n], lr=1e-3)
@@ -171,6 +176,60 @@ def cpu_epochs(workload, scale, steps, warmup, drop_rate=0.3):
             "ms_per_step": 1e3 * t / len(times), "q": q}
 
 
+def reference_epochs(workload, scale, steps, warmup, drop_rate=0.3, sample_perc=SAMPLE_PERC, pipeline="hybrid",
+                     device="cpu"):
+    """The UNMODIFIED reference (training_hybrid.train / training_straight_through.train + model.GNNModel from
+    oracle/_ref or /root/reference, on the pure-torch PyG stand-in of oracle/shim) on a bounded sample of the workload:
+    stock torch-eager code path, every host core (device='cpu') or the GPU (device='cuda')."""
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    torch.manual_seed(42)
+    b = _cpu_sample(workload, scale)
+    e = b.num_edges
+    q = int(e * sample_perc)
+    f, c = b.x.size(1), b.num_classes
+    dev = torch.device(device)
+    model = ref.model.GNNModel(f, HIDDEN, c, drop_rate, "GCN").to(dev)
+    og = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-3)          # main.py:100
+    oe = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-3)  # main.py:122
+    oa = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)                            # main.py:123
+    args = make_args(dev, drop_rate)
+    args.pipeline = pipeline
+    args.hybrid_checkpoint = True      # the configuration of the reference's own Reddit logs (BASELINE.md section 1)
+    mod = ref.training_straight_through if pipeline == "straight_through" else ref.training_hybrid
+    crit = nn.CrossEntropyLoss()
+    if dev.type == "cuda":
+        b = b.to(dev)
+    times, learned = [], 0
+    for it in range(warmup + steps):
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, n_cond, _ = mod.train(args, 1 + it, 1000, model, og, oe, oa, crit, [b], q=q, alternate_frequency=0)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            learned += n_cond
+    t = sum(times)
+    return {"value": q * len(times) / t, "unit": "edges/s", "cores": torch.get_num_threads() if dev.type == "cpu" else 0,
+            "kind": "reference",
+            "sample": f"{workload} shape scaled {scale:g}x (N={b.num_nodes}, E={e}, q={q}, F={f}, H={HIDDEN}), "
+                      f"{len(times)} epochs of the reference's own {mod.__name__}.train (hybrid_checkpoint on, natural "
+                      f"gate: {learned} learned-wins steps) + model.GNNModel on the pure-torch GCNConv stand-in, "
+                      f"dropout {drop_rate}, device {dev.type}",
+            "ms_per_step": 1e3 * t / len(times), "q": q}
+
+
+def host_baseline(a, steps, warmup):
+    """kind 'reference' whenever the reference modules are present (oracle/_ref travels to the GPU box), else the port."""
+    from oracle import ref_loader
+    if ref_loader.available() and not os.environ.get("SGS_CPU_PORT"):
+        return reference_epochs(a.workload, a.cpu_scale, steps, warmup, a.drop_rate, a.sample_perc, a.pipeline)
+    return cpu_epochs(a.workload, a.cpu_scale, steps, warmup, a.drop_rate, a.sample_perc)
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -181,12 +240,15 @@ def run_reference_arm(a):
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
         torch.set_num_threads(os.cpu_count() or 1)
-    r = cpu_epochs(a.workload, scale, a.steps, a.warmup)
+    if a.ref_device == "cuda":      # stock torch-eager reference on this GPU (a second stated baseline)
+        r = reference_epochs(a.workload, scale, a.steps, a.warmup, a.drop_rate, a.sample_perc, a.pipeline, "cuda")
+    else:
+        r = host_baseline(a, a.steps, a.warmup)
     line = {"impl": "reference", "metric": "sampled_edges_per_s", "value": r["value"], "unit": "edges/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{a.workload}-shape hybrid epoch (bounded CPU sample)", "sample": r["sample"],
-                       "hidden": HIDDEN, "sample_perc": SAMPLE_PERC},
+            "config": {"workload": f"{a.workload}-shape {a.pipeline} epoch (bounded sample, device {a.ref_device})",
+                       "sample": r["sample"], "hidden": HIDDEN, "sample_perc": a.sample_perc, "pipeline": a.pipeline},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -196,6 +258,62 @@ def run_reference_arm(a):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+
+CHK_SEED_RAND, CHK_SEED_LEARN = 0x5EED0001, 0x5EED0002
+
+
+def selection_checksum(model, batch, q, shard, coef=0.3):
+    """64-bit checksum of the GLOBAL ids of the edges the learned sampler selects at a fixed step: freshly initialised
+    weights (torch seed 42), dropout off, Exp(1) noise of fixed seeds keyed by global edge id.  The same value at
+    every GPU count shows the destination-sharded select (digit-histogram all-reduce, global-id tie-break) picks
+    exactly the single-GPU edge set (training_hybrid.py:45-83, sampling.py:91-155)."""
+    import torch.distributed as dist
+    from sgs_gnn_b200 import ops
+    from sgs_gnn_b200._lib import SAMPLE_RAW, SAMPLE_TRAIN
+    scorer = model.edge_prob_mlp
+    was_training = model.training
+    model.eval()
+    fc1, fc2 = scorer.fc1, scorer.fc2
+    with torch.no_grad():
+        if shard:
+            from sgs_gnn_b200 import dist as sdist, sharded
+            lg = batch.local
+            dev = batch.x.device
+            e_loc = lg.graph.num_edges
+            topq = sdist.DistributedTopQ(sdist.CudaTopQOps(persistent=True), group=batch.comm.group)
+            r = topq.select_ex(batch.scores, None, ops.exponential(e_loc, dev, CHK_SEED_RAND, gid=batch.gid), q,
+                               SAMPLE_RAW, 0.0, gid=batch.gid)
+            out = sharded.embed(scorer, batch.x, lg.subgraph(r.sel))
+            p = ops.edge_score_forward(out, lg.graph, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
+                                       fc2.bias.reshape(-1), None, 0.0, 0)
+            smp = topq.select_ex(p, batch.prob, ops.exponential(e_loc, dev, CHK_SEED_LEARN, gid=batch.gid), q,
+                                 SAMPLE_TRAIN, coef, gid=batch.gid)
+            gids = batch.gid[smp.sel.long()]
+            tau_bits = smp.tau_bits
+        else:
+            n, e, dev = batch.x.size(0), batch.edge_index.size(1), batch.x.device
+            g_full = ops.graph_of(batch.edge_index, n)
+            r = ops.sample_topq(ops.softmax_f32(batch.prob), None, q, SAMPLE_RAW, 0.0,
+                                noise=ops.exponential(e, dev, CHK_SEED_RAND))
+            out = scorer.embed(batch.x, g_full.subgraph(r.sel, ascending=True))
+            p = ops.edge_score_forward(out, g_full, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
+                                       fc2.bias.reshape(-1), None, 0.0, 0)
+            smp = ops.sample_topq(p, batch.prob, q, SAMPLE_TRAIN, coef, noise=ops.exponential(e, dev, CHK_SEED_LEARN))
+            gids = smp.sel.long()
+            tau_bits = int(smp.state[2].item()) & 0xFFFFFFFF
+        # order-independent: sum over the selected ids of an affine hash modulo the Mersenne prime 2^61 - 1
+        # (g < 2^31, multiplier < 2^29: no int64 overflow before the modulo); int64 sums wrap deterministically
+        h = (gids * 0x1B873593 + 0x52DCE729) % ((1 << 61) - 1)
+        tot = torch.stack([h.sum(), gids.sum(), torch.tensor(gids.numel(), device=gids.device)])
+        if shard:
+            dist.all_reduce(tot)
+        tot = tot.cpu()
+    model.train(was_training)
+    return {"hash": f"{int(tot[0]) & 0xFFFFFFFFFFFFFFFF:016x}", "id_sum": int(tot[1]), "count": int(tot[2]),
+            "tau_bits": f"{tau_bits & 0xFFFFFFFF:08x}",
+            "how": "edges selected by the learned sampler on freshly initialised weights (seed 42), dropout off, "
+                   "noise seeds fixed and keyed by global edge id; identical for every --gpus N"}
+
 
 def run_gpu_arm(a):
     import torch.distributed as dist
@@ -224,10 +342,11 @@ def run_gpu_arm(a):
         # weak scaling: every rank trains on its own replica graph (seed differs per rank)
         batch = synth.make_graph(a.workload, seed=42 + rank, device=dev, scale=a.scale)
         n, e, f, c = batch.num_nodes, batch.num_edges, batch.x.size(1), batch.num_classes
-    q = int(e * SAMPLE_PERC)
+    q = int(e * a.sample_perc)
     units = 1 if shard else world     # graphs processed per step over all ranks
     model, og, oe, oa = build_model(f, c, dev, a.drop_rate)
     args = make_args(dev, a.drop_rate)
+    chk = selection_checksum(model, batch, q, shard) if (shard or world == 1) else None
     args.data_parallel = world > 1 and not shard   # independent graph batches per rank + weight-gradient all-reduce
     # The reference's conditional gate (training_hybrid.py:92-101) skips the scorer backward whenever the random
     # baseline wins, which makes a step ~2x cheaper.  By default the bench computes the gate (both forwards, the
@@ -391,10 +510,15 @@ def run_gpu_arm(a):
                              "achieved_gbs": (e_k1 * 1032 + n * 1028) / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0,
                              "peak_gbs": pk["hbm"]}}
     shares = {k: round(v[0] / ms, 4) for k, v in sorted(ktot.items(), key=lambda kv: -kv[1][0])}
+    # measured DRAM bytes per launch (ncu --set full capture of this very command, newest round first); a CONSTANT
+    # copied from profiles/, valid for the Reddit shape on one GPU only -- labelled as such in `traffic_source`
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.isfile(tpath) and a.workload == "reddit" and a.scale == 1.0 and world == 1:
-        traffic = json.load(open(tpath))
+    for tag in ("r02", "r01"):
+        tpath = os.path.join(ROOT, "profiles", f"{tag}_traffic.json")
+        if os.path.isfile(tpath) and a.workload == "reddit" and a.scale == 1.0 and world == 1 and \
+                a.pipeline == "hybrid" and a.sample_perc == SAMPLE_PERC:
+            traffic = json.load(open(tpath))
+            break
     if "edge_score_fwd" in traffic:
         tr = traffic["edge_score_fwd"]
         roofline["traffic"] = (tr["dram_read_gb"] + tr["dram_write_gb"]) * 1e9
@@ -424,25 +548,35 @@ def run_gpu_arm(a):
         avg_s = t_ms / cnt * 1e-3
         peak = pk["tensor"] if bound == "tensor" else pk["hbm"]
         ach = work / avg_s / (1e12 if bound == "tensor" else 1e9)
+        # two views: `frac_algorithmic` divides SURVEY 8(d)-bis's no-reuse byte model (every gathered row counted once
+        # per edge) by the time -- it exceeds 1 when L1/L2 serve repeated row gathers; `frac_dram` divides the DRAM
+        # bytes ncu measured for the same launch by the same time -- the fraction of the HBM roofline actually used.
+        # `frac` is the DRAM view where it exists (HBM-bound kernels), the algorithmic view otherwise.
         ent = {"kernel": name, "bound": bound, "launches": cnt, "avg_launch_ms": t_ms / cnt, "achieved": ach,
-               "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak}
+               "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac_algorithmic": ach / peak,
+               "frac_dram": None, "frac": ach / peak}
         if name in traffic:
             ent["traffic"] = (traffic[name]["dram_read_gb"] + traffic[name]["dram_write_gb"]) * 1e9
+            ent["frac_dram"] = ent["traffic"] / avg_s / 1e9 / pk["hbm"]
+            if bound == "hbm":
+                ent["frac"] = ent["frac_dram"]
         kernels.append(ent)
 
     cpu = None
     if not a.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only (rank 0 is the only rank there)
-        cpu = cpu_epochs(a.workload, a.cpu_scale, 2, 1, a.drop_rate)
+        cpu = host_baseline(a, 2, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": "sampled_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "extra_warmup": extra, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "strong" if shard else "weak",
+            # N > 1 shards ONE fixed graph (strong scaling) unless --parallel dp; the N = 1 point of that curve is the
+            # same fixed graph, so it carries the same label
+            "scaling": "strong" if a.parallel == "shard" else "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32"}.get(a.precision, a.precision), "data": "synthetic",
             "config": {"workload": f"{a.workload}-shape hybrid epoch, single full-graph batch" +
                                    ("" if a.scale == 1.0 else f" (scaled {a.scale:g}x)"),
                        "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
-                       "sample_perc": SAMPLE_PERC, "drop_rate": a.drop_rate, "pipeline": a.pipeline,
+                       "sample_perc": a.sample_perc, "drop_rate": a.drop_rate, "pipeline": a.pipeline,
                        "conditional": True,
                        "gate": ("forced learned-wins: both forwards + gate are computed, then every step runs the full "
                                 "learned branch incl. the scorer backward" if a.gate == "learned" else "natural"),
@@ -456,7 +590,7 @@ def run_gpu_arm(a):
                        "learned_wins_steps": learned},
             "epochs_per_s": units * a.steps / (ms * 1e-3), "scored_edges_per_s": units * e * a.steps / (ms * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": int(mallocs),
-            "roofline": roofline,
+            "roofline": roofline, "sel_checksum": chk,
             "kernel_time_share": shares, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -483,6 +617,9 @@ def main():
                     help="learned: every step takes the learned-wins branch (full work); natural: the reference's gate")
     ap.add_argument("--pipeline", default="hybrid", choices=["hybrid", "straight_through"],
                     help="hybrid (BASELINE.json's metric) or straight_through (dense scorer backward over all E edges)")
+    ap.add_argument("--sample-perc", type=float, default=SAMPLE_PERC, help="edge budget q / E (Scripts/run_sparsity.sh)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: host cores (the driver's arm) or stock torch-eager on this GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

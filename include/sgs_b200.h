@@ -204,6 +204,9 @@ int32_t sgs_softmax_f32(const float* in, int64_t n, float* out, void* ws, size_t
                         sgs_stream_t stream);
 /* noise[i] = Exp(1) sample from a counter-based generator keyed (seed, i). */
 int32_t sgs_exponential_f32(float* noise, int64_t n, uint64_t seed, sgs_stream_t stream);
+/* noise[i] = element gid[i] of the contiguous draw above (same seed): the noise of a destination-sharded edge
+ * list keyed by GLOBAL edge id, so the sampled set does not depend on the number of shards. */
+int32_t sgs_exponential_ids_f32(float* noise, const int64_t* gid, int64_t n, uint64_t seed, sgs_stream_t stream);
 
 /* state layout (device, int64[8]): [0]=prefix bits so far, [1]=remaining k, [2]=tau bits,
  * [3]=#keys > tau, [4]=#ties to take, [5]=invalid-input flag, [6]=#keys == tau, [7]=reserved */

@@ -47,6 +47,7 @@ SIGNATURES = {
     "sgs_sum_f32": (I32, [P, I64, P, P, SZ, P]),
     "sgs_softmax_f32": (I32, [P, I64, P, P, SZ, P]),
     "sgs_exponential_f32": (I32, [P, I64, U64, P]),
+    "sgs_exponential_ids_f32": (I32, [P, P, I64, U64, P]),
     "sgs_topq_keys": (I32, [P, P, P, I64, F32, F32, I32, P, P, P, P, P]),
     "sgs_topq_find": (I32, [P, P, I64, I32, P]),
     "sgs_topq_hist": (I32, [P, I64, P, P, I32, P]),

@@ -60,10 +60,18 @@ def _ce(criterion, out, batch, tm_u8, acc=None):
     return criterion(out[batch.train_mask], batch.y[batch.train_mask])
 
 
-def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, backward_fn):
-    """One learned step on a device-resident batch.  Returns (loss tensor, update_edge_mlp)."""
+def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, backward_fn, checks=None):
+    """One learned step on a device-resident batch.  Returns (loss tensor, update_edge_mlp).
+    `checks`: a list the step appends device-side validity flags to (sampler state vectors, the edge list's
+    out-of-range flag) that it has NOT read itself; the caller reads them together with the loss value."""
     n = batch.x.size(0)
     g_full = ops.graph_of(batch.edge_index, n)
+    oob = g_full.take_oob_flag()
+    if oob is not None:
+        if checks is not None:
+            checks.append(("oob", oob))
+        elif int(oob.item()) != 0:
+            raise RuntimeError("edge_index contains node ids outside [0, num_nodes)")
     tm_u8 = batch.train_mask.view(torch.uint8)
     scorer = model.edge_prob_mlp
     dp = sdist.is_dist() and bool(getattr(args, "data_parallel", False))
@@ -78,20 +86,17 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
 
     # pass 1: probabilities of ALL edges (training_hybrid.py:51-64), no autograd tape
     profiler = getattr(model, "gpu_profiler", None)
-    if profiler is not None:
-        profiler.begin("edge_mlp_pre")
+    ops.seg_begin(profiler, "edge_mlp_pre")
     out = scorer.embed(batch.x, g_rand if g_rand is not None else g_full)
-    if profiler is not None:
-        profiler.end("edge_mlp_pre")
-        profiler.begin("edge_score")
+    ops.seg_end(profiler, "edge_mlp_pre")
+    ops.seg_begin(profiler, "edge_score")
     seed_sc = ops.next_seed()
     p_drop = scorer._drop()
     fc1, fc2 = scorer.fc1, scorer.fc2
     with torch.no_grad():
         p_full = ops.edge_score_forward(out.detach(), g_full, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
                                         fc2.bias.reshape(-1), None, p_drop, seed_sc)
-    if profiler is not None:
-        profiler.end("edge_score")
+    ops.seg_end(profiler, "edge_score")
 
     # sample (training_hybrid.py:72-83)
     smp = sampling.sample_edges(p_full, batch.prob, q, False, coef, validate=False)
@@ -135,6 +140,17 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
         update_edge_mlp = bool(host[32] > host[33])
         if getattr(args, "force_branch", None) == "learned":   # bench only: always time the full (learned-wins) step
             update_edge_mlp = True
+        elif getattr(args, "force_branch", None) == "random":  # tests only: a random-wins step on demand
+            update_edge_mlp = False
+    elif checks is not None:
+        # no gate read on this path: the sampler's invalid-input / count flags ride on the caller's loss read
+        checks.append(("sampler", smp.state))
+        if r is not None:
+            checks.append(("sampler", r.state))
+    else:
+        _check_sampler(smp.state.cpu(), q)
+        if r is not None:
+            _check_sampler(r.state.cpu(), q)
     if update_edge_mlp:
         loss = ops.fused_loss(learned_out, batch.y, tm_u8, p_s if with_edges else None, g_s if with_edges else None,
                               args.regularizer1_coef, args.consist_reg_coef, bool(args.reg1), bool(args.reg2),
@@ -143,6 +159,31 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
         loss = _ce(criterion, random_out, batch, tm_u8, acc_r)
     backward_fn(loss)
     return loss, update_edge_mlp
+
+
+def _defer_oob(batch, checks):
+    """Queue the out-of-range flag of batch.edge_index (set once, when the edge list was narrowed to int32)."""
+    f = ops.graph_of(batch.edge_index, batch.x.size(0)).take_oob_flag()
+    if f is not None:
+        checks.append(("oob", f))
+
+
+def _read_loss_and_checks(loss, checks, q):
+    """ONE device->host read for the step's loss value and every deferred validity flag; raises the way the
+    reference does (torch.multinomial's RuntimeError, PyG's index assert) -- after the step, without an extra sync."""
+    if not checks:
+        return loss.item()
+    parts = [loss.detach().reshape(1).double()] + [t.reshape(-1).double() for _, t in checks]
+    host = torch.cat(parts).cpu()
+    off = 1
+    for kind, t in checks:
+        k = t.numel()
+        if kind == "sampler":
+            _check_sampler(host[off:off + k], q)
+        elif kind == "oob" and int(host[off]) != 0:
+            raise RuntimeError("edge_index contains node ids outside [0, num_nodes)")
+        off += k
+    return float(host[0])
 
 
 def _check_sampler(st, q):
@@ -164,13 +205,20 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
     total_update = 0
 
     def _backward(loss):
-        if profiler is not None:
-            profiler.begin("backward")
+        ops.seg_begin(profiler, "backward")
         loss.backward()
-        if profiler is not None:
-            profiler.end("backward")
+        ops.seg_end(profiler, "backward")
 
+    dp_mode = sdist.is_dist() and bool(getattr(args, "data_parallel", False)) and mode == "learned"
     for batch in cluster_loader:
+        checks = []
+        if dp_mode and not isinstance(batch, sharded.ShardedBatch):
+            # data-parallel ranks must issue the same collectives: agree on the control flow of this iteration first
+            any_tr, all_tr, any_big, all_big = sdist.agree_on_path(_has_train(batch), batch.edge_index.shape[1] > q)
+            if any_tr != all_tr or any_big != all_big:
+                raise RuntimeError("data-parallel ranks disagree on this iteration's path (a batch without train "
+                                   "nodes or with E <= q on some ranks only): give every rank batches of the same "
+                                   "kind per iteration (main.py:41-67 cluster batches), or train them on one rank")
         if not _has_train(batch):
             continue
         total_update += 1
@@ -207,7 +255,7 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
                 r_ = (args.t_init - args.t_min) / max_epoch
                 temperature = max(args.t_min, args.t_init - epoch * r_)
                 loss, update_edge_mlp = learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q,
-                                                     _backward)
+                                                     _backward, checks)
                 if sdist.is_dist() and bool(getattr(args, "data_parallel", False)):
                     opts = (optimizer_edge_prob, optimizer_gnn) if update_edge_mlp else (optimizer_gnn,)
                     seen, plist = set(), []
@@ -226,12 +274,14 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
                     optimizer_gnn.step()
             else:
                 batch = batch.to(device)
+                _defer_oob(batch, checks)
                 out = model(batch, batch.edge_index)
                 loss = _ce(criterion, out, batch, batch.train_mask.view(torch.uint8))
                 _backward(loss)
                 optimizer_gnn.step()
         elif mode in ("random", "edge", "full"):
             batch = batch.to(device)
+            _defer_oob(batch, checks)
             ei = batch.edge_index
             if mode == "random" and ei.shape[1] > q:
                 ei = sampling.random_edge_sampling(ei, q=q)
@@ -245,6 +295,6 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
         else:
             raise ValueError("Invalid mode. Choose 'learned', 'random', or 'full'.")
 
-        total_loss += loss.item()
+        total_loss += _read_loss_and_checks(loss, checks, q)
 
     return total_loss / len(cluster_loader), temperature, conditional_update, total_update

@@ -3,6 +3,8 @@
 // The parity mode works in bounded edge chunks: features -> fp32 GEMM -> fused epilogue, and for
 // the backward: recompute -> dA -> dF = dA.W1, dW1 += dA^T.F -> scatter into d_out.
 // The tensor-core (tcgen05) forward lives in edge_score_tc.cu.
+// precision == SGS_PREC_TF32 ("tensor-core parity mode"): the same chunked pipeline with its three contractions on
+// the tcgen05 kind::tf32 GEMM (gemm_tc.cu) and chunks small enough that F and Z stay L2-resident between kernels.
 #include "common.cuh"
 
 namespace sgs {
@@ -25,6 +27,14 @@ static inline bool tc_bwd_supported(int32_t precision, int64_t H) {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int64_t kMaxChunk = 131072;
+constexpr int64_t kMaxChunkTf32 = 32768;   // F (64 MB at H = 256) + Z (32 MB) of a chunk fit the 126 MB L2
+static inline bool is_16bit(int32_t precision) { return precision == SGS_PREC_BF16 || precision == SGS_PREC_FP16; }
+
+// Wt[c, r] = W[r, c]   (W [R, C] row-major; tiny: H x 2H)
+__global__ void transpose_small_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ Wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R * C) Wt[(int64_t)(i % C) * R + i / C] = W[i];
+}
 
 // F[i, c] = x*y, F[i, H+c] = x-y   (one warp per edge, float4 columns)
 __global__ void __launch_bounds__(kThreads)
@@ -199,10 +209,11 @@ extern "C" {
 
 size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t N, int64_t H, int32_t precision, int32_t backward) {
   if (n <= 0 || H <= 0) return 256;
-  if (precision != SGS_PREC_FP32 && !backward) return edge_score_tc_workspace_bytes(n, N, H);
+  if (is_16bit(precision) && !backward) return edge_score_tc_workspace_bytes(n, N, H);
   if (backward && tc_bwd_supported(precision, H)) return edge_score_bwd_tc_workspace_bytes(n, N, H);
-  const int64_t chunk = n < kMaxChunk ? n : kMaxChunk;
-  return (size_t)chunk * per_edge_bytes(H, backward) + 256;
+  const int64_t cap = precision == SGS_PREC_TF32 ? kMaxChunkTf32 : kMaxChunk;
+  const int64_t chunk = n < cap ? n : cap;
+  return (size_t)chunk * per_edge_bytes(H, backward) + 256 + (size_t)2 * H * H * sizeof(float) + 256;
 }
 
 int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
@@ -214,12 +225,14 @@ int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t
   SGS_CHECK_ARG(out && src && dst && W1 && b1 && w2 && b2 && p && ws, "null pointer");
   SGS_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "p_drop must be in [0,1)");
   cudaStream_t st = as_stream(stream);
-  if (precision != SGS_PREC_FP32)
+  if (is_16bit(precision))
     return edge_score_fwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, ws, ws_bytes,
                              precision, st);
+  SGS_CHECK_ARG(precision == SGS_PREC_FP32 || precision == SGS_PREC_TF32, "unknown precision");
+  const int32_t gprec = precision == SGS_PREC_TF32 ? SGS_PREC_TF32 : SGS_PREC_FP32;
   const size_t pe = per_edge_bytes(H, 0);
   int64_t chunk = (int64_t)((ws_bytes > 256 ? ws_bytes - 256 : 0) / pe);
-  if (chunk > kMaxChunk) chunk = kMaxChunk;
+  if (chunk > (gprec == SGS_PREC_TF32 ? kMaxChunkTf32 : kMaxChunk)) chunk = gprec == SGS_PREC_TF32 ? kMaxChunkTf32 : kMaxChunk;
   if (chunk > n) chunk = n;
   if (chunk < 1) { set_error("sgs_edge_score_fwd: workspace too small"); return SGS_E_WORKSPACE; }
   float* F = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -228,7 +241,7 @@ int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t
     const int64_t m = (n - e0 < chunk) ? n - e0 : chunk;
     edge_feat_kernel<<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
     SGS_LAUNCH_CHECK();
-    int32_t rc = sgs_gemm(F, 2 * H, 1, W1, 2 * H, 1, Z, H, m, H, 2 * H, 0, SGS_PREC_FP32, stream);
+    int32_t rc = sgs_gemm(F, 2 * H, 1, W1, 2 * H, 1, Z, H, m, H, 2 * H, 0, gprec, stream);
     if (rc) return rc;
     edge_hidden_kernel<false><<<edge_grid(m), kThreads, 0, st>>>(Z, (int)H, b1, w2, b2, ids, e0, m, p_drop, seed,
                                                                  p + e0, nullptr, nullptr, nullptr, nullptr);
@@ -255,29 +268,40 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
     return edge_score_bwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, dw2,
                              db2, ws, ws_bytes, precision, st);
   }
+  SGS_CHECK_ARG(precision == SGS_PREC_FP32 || precision == SGS_PREC_TF32 || is_16bit(precision), "unknown precision");
+  // kind::tf32 needs 16-byte aligned rows; 16-bit modes at widths the fused kernels do not cover use fp32
+  const bool tf32 = precision == SGS_PREC_TF32;
+  const int32_t gprec = tf32 ? SGS_PREC_TF32 : SGS_PREC_FP32;
   const size_t pe = per_edge_bytes(H, 1);
-  int64_t chunk = (int64_t)((ws_bytes > 256 ? ws_bytes - 256 : 0) / pe);
-  if (chunk > kMaxChunk) chunk = kMaxChunk;
+  const size_t wt_bytes = (size_t)2 * H * H * sizeof(float) + 256;
+  int64_t chunk = (int64_t)((ws_bytes > 256 + wt_bytes ? ws_bytes - 256 - wt_bytes : 0) / pe);
+  if (chunk > (tf32 ? kMaxChunkTf32 : kMaxChunk)) chunk = tf32 ? kMaxChunkTf32 : kMaxChunk;
   if (chunk > n) chunk = n;
   if (chunk < 1) { set_error("sgs_edge_score_bwd: workspace too small"); return SGS_E_WORKSPACE; }
   float* F = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   float* Z = F + chunk * 2 * H;   // becomes dA
   float* dF = Z + chunk * H;
+  float* W1t = (float*)(((uintptr_t)(dF + chunk * 2 * H) + 255) & ~(uintptr_t)255);   // [2H, H]
+  if (tf32) {
+    transpose_small_kernel<<<(unsigned)ceil_div(2 * H * H, 256), 256, 0, st>>>(W1, (int)H, (int)(2 * H), W1t);
+    SGS_LAUNCH_CHECK();
+  }
   const size_t shmem = (size_t)(2 * H + 1) * sizeof(float);
   for (int64_t e0 = 0; e0 < n; e0 += chunk) {
     const int64_t m = (n - e0 < chunk) ? n - e0 : chunk;
     edge_feat_kernel<<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
     SGS_LAUNCH_CHECK();
-    int32_t rc = sgs_gemm(F, 2 * H, 1, W1, 2 * H, 1, Z, H, m, H, 2 * H, 0, SGS_PREC_FP32, stream);
+    int32_t rc = sgs_gemm(F, 2 * H, 1, W1, 2 * H, 1, Z, H, m, H, 2 * H, 0, gprec, stream);
     if (rc) return rc;
     edge_hidden_kernel<true><<<edge_grid(m), kThreads, shmem, st>>>(Z, (int)H, b1, w2, b2, ids, e0, m, p_drop, seed,
                                                                     nullptr, dp + e0, dw2, db1, db2);
     SGS_LAUNCH_CHECK();
     // dF[m,2H] = dA[m,H] . W1[H,2H]
-    rc = sgs_gemm(Z, H, 1, W1, 1, 2 * H, dF, 2 * H, m, 2 * H, H, 0, SGS_PREC_FP32, stream);
+    if (tf32) rc = sgs_gemm(Z, H, 1, W1t, H, 1, dF, 2 * H, m, 2 * H, H, 0, SGS_PREC_TF32, stream);   // NT vs W1^T
+    else rc = sgs_gemm(Z, H, 1, W1, 1, 2 * H, dF, 2 * H, m, 2 * H, H, 0, SGS_PREC_FP32, stream);
     if (rc) return rc;
-    // dW1[H,2H] += dA^T[H,m] . F[m,2H]
-    rc = sgs_gemm(Z, 1, H, F, 1, 2 * H, dW1, 2 * H, H, 2 * H, m, 1, SGS_PREC_FP32, stream);
+    // dW1[H,2H] += dA^T[H,m] . F[m,2H]   (TN form: both operands unit-stride along M / N)
+    rc = sgs_gemm(Z, 1, H, F, 1, 2 * H, dW1, 2 * H, H, 2 * H, m, 1, gprec, stream);
     if (rc) return rc;
     edge_feat_bwd_kernel<<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, dF, d_out);
     SGS_LAUNCH_CHECK();

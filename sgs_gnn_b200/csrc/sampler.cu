@@ -635,6 +635,18 @@ __global__ void exponential_kernel(float* __restrict__ out, int64_t n, uint64_t 
   }
 }
 
+// noise for the edges with GLOBAL ids gid[i]: the value exponential_kernel gives element gid[i] of a contiguous draw,
+// so a destination-sharded edge list sees exactly the noise of the unsharded one (identical keys for any rank count)
+__global__ void exponential_ids_kernel(float* __restrict__ out, const int64_t* __restrict__ gid, int64_t n,
+                                       uint64_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t g = (uint64_t)gid[i];
+    const uint64_t r = splitmix64(seed ^ splitmix64(g >> 1));
+    const uint32_t w = (g & 1) ? (uint32_t)(r >> 32) : (uint32_t)r;
+    out[i] = -logf(((float)(w >> 9) + 0.5f) * (1.0f / 8388608.0f));
+  }
+}
+
 __global__ void gather_selected_kernel(const float* __restrict__ p, const float* __restrict__ prob,
                                        const int32_t* __restrict__ sel, int64_t q, float c_p, float c_prob,
                                        int mode, const float* __restrict__ S, float* __restrict__ p_sel,
@@ -712,6 +724,14 @@ int32_t sgs_exponential_f32(float* noise, int64_t n, uint64_t seed, sgs_stream_t
   SGS_CHECK_ARG(n >= 0 && (n == 0 || noise), "bad arguments");
   if (n == 0) return SGS_OK;
   exponential_kernel<<<stream_grid((n + 1) / 2, 256, 8), 256, 0, as_stream(stream)>>>(noise, n, seed);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_exponential_ids_f32(float* noise, const int64_t* gid, int64_t n, uint64_t seed, sgs_stream_t stream) {
+  SGS_CHECK_ARG(n >= 0 && (n == 0 || (noise && gid)), "bad arguments");
+  if (n == 0) return SGS_OK;
+  exponential_ids_kernel<<<stream_grid(n, 256, 8), 256, 0, as_stream(stream)>>>(noise, gid, n, seed);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }

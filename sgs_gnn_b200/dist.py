@@ -246,18 +246,46 @@ def allreduce_gate(learned_correct, random_correct):
 
 
 def allreduce_grads(params, average=True):
-    """One flat all-reduce of the gradients of `params` (those that have one)."""
+    """One flat all-reduce of the gradients of `params`.  The buffer layout is the same on every rank whatever its
+    local has-grad pattern (a rank without a gradient contributes zeros, the has-grad bitmap rides along), so ranks
+    can never issue mismatched collectives; a parameter without a gradient on EVERY rank keeps grad = None."""
     if not is_dist():
         return
-    gs = [p.grad for p in params if p.grad is not None]
-    if not gs:
+    ps = [p for p in params if p.requires_grad]
+    if not ps:
         return
-    flat = torch.cat([g.reshape(-1) for g in gs])
-    dist.all_reduce(flat)
+    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in ps], dtype=torch.float32, device=ps[0].device)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
+                      for p in ps] + [has])
+    staged = flat.is_cuda and dist.get_backend() == "gloo"
+    if staged:
+        c = flat.cpu()
+        dist.all_reduce(c)
+        flat.copy_(c)
+    else:
+        dist.all_reduce(flat)
+    seen = flat[-len(ps):].cpu()
     if average:
         flat /= dist.get_world_size()
     off = 0
-    for g in gs:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+    for i, p in enumerate(ps):
+        n = p.numel()
+        if float(seen[i]) > 0.0:
+            if p.grad is None:
+                p.grad = flat[off:off + n].view_as(p).clone()
+            else:
+                p.grad.copy_(flat[off:off + n].view_as(p))
         off += n
+
+
+def agree_on_path(has_train, big):
+    """Data-parallel ranks decide control flow BEFORE any collective of the step (training_hybrid.py:29-30 `continue`
+    on a batch without train nodes, :41 the E > q branch): one 4-int all-reduce tells every rank what the others
+    would do.  Returns (any_has_train, all_has_train, any_big, all_big)."""
+    t = torch.tensor([int(has_train), -int(has_train), int(big), -int(big)], dtype=torch.int64)
+    if is_dist():
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = t.cpu()
+    return bool(t[0] > 0), bool(-t[1] > 0), bool(t[2] > 0), bool(-t[3] > 0)

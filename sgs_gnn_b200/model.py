@@ -60,18 +60,15 @@ class _EdgeProbBase(nn.Module):
     def forward(self, node_features, edge_index, random_sampled_edge_index=None, use_checkpoint=False):
         profiler = getattr(self, "gpu_profiler", None)
         n = node_features.size(0)
-        if profiler is not None:
-            profiler.begin("edge_mlp_pre")
+        ops.seg_begin(profiler, "edge_mlp_pre")
         g_full = ops.graph_of(edge_index, n)
         g_msg = g_full if random_sampled_edge_index is None else ops.graph_of(random_sampled_edge_index, n)
         out = self.embed(node_features, g_msg)
-        if profiler is not None:
-            profiler.end("edge_mlp_pre")
-            profiler.begin("edge_score")
+        ops.seg_end(profiler, "edge_mlp_pre")
+        ops.seg_begin(profiler, "edge_score")
         self.last_seed = ops.next_seed()
         prob = self.score(out, g_full, seed=self.last_seed)
-        if profiler is not None:
-            profiler.end("edge_score")
+        ops.seg_end(profiler, "edge_score")
         return prob.unsqueeze(-1)
 
 
@@ -178,13 +175,11 @@ class GNNModel(nn.Module):
 
     def forward(self, data, edge_index, edge_weight=None):
         profiler = getattr(self, "gpu_profiler", None)
-        if profiler is not None:
-            profiler.begin("gnn_forward")
+        ops.seg_begin(profiler, "gnn_forward")
         x = data.x if hasattr(data, "x") else data
         g = ops.graph_of(edge_index, x.size(0))
         p_drop = float(self.dropout.p) if self.training else 0.0
         h = self.gcn1(x, g, edge_weight, relu=True, p_drop=p_drop, seed=ops.next_seed())
         out = self.gcn2(h, g, edge_weight)
-        if profiler is not None:
-            profiler.end("gnn_forward")
+        ops.seg_end(profiler, "gnn_forward")
         return out

@@ -32,6 +32,12 @@ def set_precision(gemm=None, scorer=None):
         _state["scorer"] = _PRECISION[scorer] if isinstance(scorer, str) else int(scorer)
 
 
+def scorer_supports(precision):
+    """Edge-scorer precision modes of this build: 'fp32' (CUDA cores), 'tf32' (tcgen05 kind::tf32 GEMMs on the chunked
+    fp32 pipeline: the tensor-core mode that keeps the fp32 1e-4 parity bar), 'fp16' / 'bf16' (fused tcgen05 kernels)."""
+    return precision in _PRECISION
+
+
 def get_precision():
     inv = {v: k for k, v in _PRECISION.items()}
     return {k: inv[v] for k, v in _state.items()}
@@ -131,6 +137,36 @@ class KernelTimer:
         return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
 
 
+_nvtx = bool(__import__("os").environ.get("SGS_NVTX"))
+
+
+def enable_nvtx(on=True):
+    """NVTX ranges around every kernel family (the names bench.py's kernel_time_share uses) and around the
+    reference's profiler segments (utils.GpuMemoryProfiler: edge_mlp_pre, edge_score, gnn_forward, backward), so an
+    nsys / ncu timeline is readable.  Off by default (SGS_NVTX=1 turns it on at import)."""
+    global _nvtx
+    _nvtx = bool(on)
+
+
+def nvtx_enabled():
+    return _nvtx
+
+
+def seg_begin(profiler, name):
+    """Start of one of the reference's profiler segments (utils.py:13-80 names): NVTX range + memory profiler."""
+    if _nvtx:
+        torch.cuda.nvtx.range_push(name)
+    if profiler is not None:
+        profiler.begin(name)
+
+
+def seg_end(profiler, name):
+    if profiler is not None:
+        profiler.end(name)
+    if _nvtx:
+        torch.cuda.nvtx.range_pop()
+
+
 class _timed:
     __slots__ = ("name", "a")
 
@@ -138,11 +174,15 @@ class _timed:
         self.name = name
 
     def __enter__(self):
+        if _nvtx:
+            torch.cuda.nvtx.range_push(self.name)
         if _timer is not None:
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record()
 
     def __exit__(self, *exc):
+        if _nvtx:
+            torch.cuda.nvtx.range_pop()
         if _timer is not None:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
@@ -203,6 +243,13 @@ class Graph:
         self._mean_w = None       # SAGEConv mean-aggregation weights in both CSR orders (lazily built)
         self._norm_unw = None
         self._norm_w = None  # (weakref to weight tensor, version, GcnNorm)
+        self.oob_flag = None      # device int32 [1] set by sgs_edge_index_split when an id lies outside [0, N)
+
+    def take_oob_flag(self):
+        """The not-yet-checked out-of-range flag of this edge list (device int32 [1]) or None; the caller folds it
+        into a host read it performs anyway (end of the training step) and raises like PyG's device assert would."""
+        f, self.oob_flag = self.oob_flag, None
+        return f
 
     @staticmethod
     def from_edge_index(edge_index, num_nodes, validate=False):
@@ -217,7 +264,10 @@ class Graph:
               "sgs_edge_index_split")
         if validate and int(flag.item()) != 0:
             raise RuntimeError("edge_index contains node ids outside [0, num_nodes)")
-        return Graph(src, dst, num_nodes, ei)
+        g = Graph(src, dst, num_nodes, ei)
+        if not validate:
+            g.oob_flag = flag
+        return g
 
     @property
     def src_sorted(self):
@@ -648,10 +698,16 @@ def softmax_f32(x):
     return out
 
 
-def exponential(n, device, seed=None):
+def exponential(n, device, seed=None, gid=None):
+    """Exp(1) noise from the counter-based generator keyed (seed, edge id).  `gid` (int64 [n], global edge ids of a
+    shard): element i is the value the contiguous draw gives edge gid[i], whatever the number of shards."""
     out = torch.empty(n, dtype=torch.float32, device=device)
-    check(lib().sgs_exponential_f32(_p(out), n, next_seed() if seed is None else int(seed), _stream()),
-          "sgs_exponential_f32")
+    seed = next_seed() if seed is None else int(seed)
+    if gid is not None:
+        gid = _req(gid, torch.int64, "gid")
+        check(lib().sgs_exponential_ids_f32(_p(out), _p(gid), n, seed, _stream()), "sgs_exponential_ids_f32")
+    else:
+        check(lib().sgs_exponential_f32(_p(out), n, seed, _stream()), "sgs_exponential_f32")
     return out
 
 

@@ -470,8 +470,9 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
         inj = sampling._next_noise()
         if inj is not None:
             return inj[sb.gid].contiguous()
-        return ops.exponential(e_loc, dev, seed=(ops.next_seed() + 0x9E3779B97F4A7C15 * (comm.rank + 1))
-                               & 0xFFFFFFFFFFFFFFFF)
+        # keyed by GLOBAL edge id with a seed every rank derives identically: the keys -- and with them the sampled
+        # set -- are those of the unsharded draw for any number of ranks (SURVEY 8e's invariance claim)
+        return ops.exponential(e_loc, dev, seed=ops.next_seed(), gid=sb.gid)
 
     lg_rand = None
     r = None
@@ -521,6 +522,8 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
         update_edge_mlp = bool(host[0] > host[1])
         if getattr(args, "force_branch", None) == "learned":   # bench only: always time the full (learned-wins) step
             update_edge_mlp = True
+        elif getattr(args, "force_branch", None) == "random":  # tests only: a random-wins step on demand
+            update_edge_mlp = False
     if update_edge_mlp:
         loss = ops.fused_loss(learned_out, sb.y, tm_full, p_s if with_edges else None,
                               lg_s.graph if with_edges else None, args.regularizer1_coef, args.consist_reg_coef,
@@ -532,18 +535,27 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
 
 
 def allreduce_partial_grads(params, comm):
-    """Every rank holds partial sums (over its rows / edges) of the weight gradients: one flat
-    all-reduce SUM.  Parameters without a gradient on this rank contribute zeros."""
+    """Every rank holds partial sums (over its rows / edges) of the weight gradients: one flat all-reduce SUM.
+    A parameter whose gradient is None on EVERY rank (e.g. edge_prob_mlp.gcn* on a random-wins step: they sit in
+    optimizer_gnn through main.py:100's name filter but are outside that branch's autograd graph) keeps grad = None,
+    so Adam skips it exactly as on one GPU / in the reference; the has-grad bitmap rides in the same buffer."""
     if comm.world == 1:
         return
     ps = [p for p in params if p.requires_grad]
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
+    if not ps:
+        return
+    dev = ps[0].device
+    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in ps], dtype=torch.float32, device=dev)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
+                      for p in ps] + [has])
     comm.all_reduce(flat)
+    seen = flat[-len(ps):].cpu()
     off = 0
-    for p in ps:
+    for i, p in enumerate(ps):
         k = p.numel()
-        if p.grad is None:
-            p.grad = flat[off:off + k].view_as(p).clone()
-        else:
-            p.grad.copy_(flat[off:off + k].view_as(p))
+        if float(seen[i]) > 0.0:
+            if p.grad is None:
+                p.grad = flat[off:off + k].view_as(p).clone()
+            else:
+                p.grad.copy_(flat[off:off + k].view_as(p))
         off += k

@@ -86,6 +86,37 @@ def run(rank, world, port, pipeline, conditional, edge_mlp, n, e, f, c, hdim):
             err = float((pr.grad - ps.grad).abs().max() / (pr.grad.abs().max() + 1e-20))
             worst = max(worst, err)
             assert err <= 1e-4, (k, err)
+        # ---- several optimiser steps through train(): learned-wins, then RANDOM-wins, then learned-wins again.  On a
+        # random-wins step the scorer's gcn* parameters (members of optimizer_gnn, main.py:100) have grad None; the
+        # sharded gradient all-reduce must keep it None or Adam would move them by their stale momentum ----
+        if conditional and pipeline == "hybrid":
+            from sgs_gnn_b200 import training_hybrid
+
+            def opts(m):
+                return (torch.optim.Adam([p_ for n_, p_ in m.named_parameters() if "gcn" in n_], lr=1e-2),
+                        torch.optim.Adam([p_ for n_, p_ in m.named_parameters() if "edge_prob_mlp" in n_], lr=1e-2),
+                        torch.optim.Adam(m.parameters(), lr=1e-2))
+            m_a, m_b = fresh(), fresh()
+            o_a, o_b = opts(m_a), opts(m_b)
+            g2 = torch.Generator().manual_seed(17)
+            for step, branch in enumerate(["learned", "random", "learned"]):
+                args.force_branch = branch
+                nz = [ox.exponential_noise(b.num_edges, g2).to(dev) for _ in range(2)]
+                for m_, o_, batch_ in ((m_a, o_a, b), (m_b, o_b, sb)):
+                    sampling.clear_injected()
+                    sampling.inject_noise([t.clone() for t in nz])
+                    ops.reset_seed_counter()
+                    _, _, n_cond, _ = training_hybrid.train(args, 1 + step, 10, m_, o_[0], o_[1], o_[2], crit,
+                                                           [batch_], q=q, alternate_frequency=0)
+                    assert n_cond == (1 if branch == "learned" else 0)
+            args.force_branch = None
+            worst_p = 0.0
+            for (k, pa), (_, pb) in zip(m_a.named_parameters(), m_b.named_parameters()):
+                err = float((pa - pb).abs().max() / (1.0 + pa.abs().max()))
+                worst_p = max(worst_p, err)
+                assert err <= 2e-4, (k, err)
+            if rank == 0:
+                print(f"sharded[{world}] 3 steps (learned, random, learned): max param err {worst_p:.2e}", flush=True)
         if rank == 0:
             print(f"sharded[{world}] {pipeline} cond={conditional} {edge_mlp}: loss {float(loss_sh):.6f} "
                   f"(single {float(loss_ref):.6f}), max rel grad err {worst:.2e}, learned={upd_sh}", flush=True)

@@ -192,7 +192,10 @@ def golden_mlp():
         **{"sd." + k: v for k, v in sd.items()})
 
 
-def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
+def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed, record=False):
+    """record: also store, per epoch, what the reference's training loop handed to / got back from
+    gumbel_softmax_sampling (the full edge probabilities and the selected-edge mask), so that reduced-precision
+    modes can report per-epoch probability error and sampled-set overlap against the reference."""
     b = synth.make_graph(None, seed=seed, n=n, e=e, f=f, c=c, homophily=0.7)
     q = int(e * 0.2)
     model, opt_gnn, opt_edge, opt_all = build_ref_model(f, h, c, 0.0, seed + 1)
@@ -202,6 +205,16 @@ def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
     mod = {"hybrid": ref.training_hybrid, "straight_through": ref.training_straight_through,
            "two_pass": ref.training_two_pass}[pipeline]
     losses, branch, noises = [], [], []
+    rec_p, rec_mask = [], []
+    if record:
+        inner = mod.gumbel_softmax_sampling
+
+        def spy(batch, edge_probs, *a, **kw):
+            mask, w = inner(batch, edge_probs, *a, **kw)
+            rec_p.append(edge_probs.detach().clone())
+            rec_mask.append(np.packbits(mask.numpy()))
+            return mask, w
+        mod.gumbel_softmax_sampling = spy
     for ep in range(epochs):
         torch.manual_seed(1000 + ep)
         noises.append(torch.stack([ox.exponential_noise(e), ox.exponential_noise(e)]))
@@ -211,6 +224,10 @@ def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
         losses.append(loss)
         branch.append(n_cond)
     sd1 = model.state_dict()
+    extra = {}
+    if record:
+        mod.gumbel_softmax_sampling = inner
+        extra = {"ref_p_full": torch.stack(rec_p), "ref_masks": np.stack(rec_mask)}
     # cross-check the extended oracle on the first step (same noise, dropout off)
     params = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
     st = ox.learned_step(params, b, q, noises[0][0], noises[0][1], pipeline=pipeline)
@@ -219,7 +236,7 @@ def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed):
     print(pipeline, "losses", [round(x, 5) for x in losses], "learned-wins", branch)
     npz(f"step_{tag}.npz", x=b.x, y=b.y, edge_index=b.edge_index, train_mask=b.train_mask, prob=b.prob, q=q,
         hidden=h, noises=torch.stack(noises), losses=np.array(losses), learned_wins=np.array(branch),
-        oracle_sel0=st.sel, oracle_pfull0=st.p_full,
+        oracle_sel0=st.sel, oracle_pfull0=st.p_full, **extra,
         **{"sd0." + k: v for k, v in sd0.items()}, **{"sd1." + k: v for k, v in sd1.items()})
 
 
@@ -254,7 +271,8 @@ def golden_eval():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval", "sage", "mlp"]
+    which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval", "sage", "mlp", "hybrid_h256",
+                               "st_h256"]
     if "mlp" in which:
         golden_mlp()
     if "sage" in which:
@@ -269,5 +287,9 @@ if __name__ == "__main__":
         golden_step("straight_through", "st", 300, 2400, 20, 4, 32, 6, 41)
     if "two_pass" in which:
         golden_step("two_pass", "two_pass", 300, 2400, 20, 4, 32, 6, 61)
+    if "hybrid_h256" in which:     # the benched tensor-core widths (H = 256): reduced-precision trajectory tests
+        golden_step("hybrid", "hybrid_h256", 1200, 20000, 48, 5, 256, 6, 71, record=True)
+    if "st_h256" in which:
+        golden_step("straight_through", "st_h256", 1200, 20000, 48, 5, 256, 6, 81, record=True)
     if "eval" in which:
         golden_eval()

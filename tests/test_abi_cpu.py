@@ -116,3 +116,59 @@ def test_dropin_modules_export_reference_names():
             sys.modules.pop(mod, None)
     finally:
         sys.path.remove(d)
+
+
+def test_launcher_makes_dropin_win_over_script_directory(tmp_path):
+    """`python main.py` puts the script's directory first on sys.path, so a PYTHONPATH shadow never wins.
+    The launcher installs the accelerated modules in sys.modules under the reference's names before the script runs:
+    a stand-in main.py next to decoy model.py / utils.py / sampling.py must see the sgs_gnn_b200 classes, while names
+    the build does not accelerate keep coming from the script's own modules."""
+    import subprocess
+    import sys
+    (tmp_path / "model.py").write_text("class GNNModel:\n    origin = 'decoy'\nOTHER = 'kept'\n")
+    (tmp_path / "utils.py").write_text("def calculate_f1(*a):\n    return 'decoy'\ndef plot_learning_curves():\n"
+                                       "    return 'kept'\n")
+    (tmp_path / "sampling.py").write_text("import this_module_does_not_exist\n")
+    (tmp_path / "main.py").write_text(
+        "import sys\nfrom model import *\nimport model, utils, sampling, training_hybrid\n"
+        "from utils import calculate_f1, plot_learning_curves\n"
+        "print('RESULT', GNNModel.__module__, model.OTHER, calculate_f1.__module__, plot_learning_curves(),\n"
+        "      sampling.gumbel_softmax_sampling.__module__, training_hybrid.train.__module__, sys.argv[1:])\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "sgs_gnn_b200.launch", str(tmp_path / "main.py"), "--mode", "learned"],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0]
+    assert line == ("RESULT sgs_gnn_b200.model kept sgs_gnn_b200.utils kept sgs_gnn_b200.sampling "
+                    "sgs_gnn_b200.training_hybrid ['--mode', 'learned']"), line
+    assert "sampling.py of the reference not importable" in r.stderr
+
+
+def test_launcher_overlays_the_reference_checkout():
+    """With the real reference modules present (/root/reference or oracle/_ref): the overlay keeps the reference's
+    remaining names (utils.plot_learning_curves, visualize) and replaces the accelerated ones."""
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference modules not staged")
+    from sgs_gnn_b200 import launch
+    saved = {k: sys.modules.get(k) for k in launch.ORDER}
+    saved_path = list(sys.path)
+    sys.path.insert(0, ref_loader.SHIM_DIR)      # stand-ins for torch_geometric / matplotlib (absent in this image)
+    try:
+        mods = launch.install(ref_loader.REFERENCE_DIR)
+        assert mods["model"].GNNModel.__module__ == "sgs_gnn_b200.model"
+        assert mods["utils"].calculate_f1.__module__ == "sgs_gnn_b200.utils"
+        assert hasattr(mods["utils"], "plot_learning_curves") and hasattr(mods["utils"], "visualize")
+        assert mods["training_hybrid"].train.__module__ == "sgs_gnn_b200.training_hybrid"
+        assert mods["evaluate"].ensemble_evaluate.__module__ == "sgs_gnn_b200.evaluate"
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("torch_geometric", "matplotlib"):
+                del sys.modules[k]

@@ -117,3 +117,43 @@ def _dp_worker(rank, world):
 
 def test_gradient_and_gate_allreduce():
     _run(_dp_worker, 2)
+
+
+def _dp_hetero_worker(rank, world, kind):
+    """data-parallel ranks whose batches would take different paths (no train nodes / E <= q on one rank
+    only) must not issue mismatched collectives: every rank raises the same RuntimeError before any of them."""
+    from types import SimpleNamespace
+    from sgs_gnn_b200 import _train_core, synth
+    b = synth.make_graph(None, seed=3 + rank, n=60, e=400 if (kind != "small" or rank == 0) else 40, f=4, c=2)
+    if kind == "notrain" and rank == 1:
+        b.train_mask = torch.zeros_like(b.train_mask)
+    args = SimpleNamespace(device="cpu", mode="learned", data_parallel=True, conditional=True, sparse_edge_mlp=True,
+                           t_init=0.7, t_min=0.5, degree_bias_coef=0.3, reg1=True, reg2=True,
+                           regularizer1_coef=1.0, consist_reg_coef=0.5)
+    model = torch.nn.Linear(2, 2)
+    opt = torch.optim.Adam(model.parameters())
+    with pytest.raises(RuntimeError, match="data-parallel ranks disagree"):
+        _train_core.train_epoch("hybrid", args, 1, 10, model, opt, opt, opt, torch.nn.CrossEntropyLoss(), [b], q=100)
+    dist.barrier()      # both ranks got here: nobody is stuck in a collective
+
+
+@pytest.mark.parametrize("kind", ["notrain", "small"])
+def test_data_parallel_ranks_with_different_paths_fail_together(kind):
+    _run(_dp_hetero_worker, 2, kind)
+
+
+def _dp_none_grad_worker(rank, world):
+    """A parameter with a gradient on ONE rank only still all-reduces with the same buffer layout everywhere."""
+    from sgs_gnn_b200 import dist as sdist
+    w = torch.nn.Parameter(torch.zeros(3))
+    v = torch.nn.Parameter(torch.zeros(2))
+    w.grad = torch.full((3,), 2.0)
+    if rank == 0:
+        v.grad = torch.full((2,), 4.0)
+    sdist.allreduce_grads([w, v])
+    assert torch.allclose(w.grad, torch.full((3,), 2.0))
+    assert v.grad is not None and torch.allclose(v.grad, torch.full((2,), 2.0))
+
+
+def test_gradient_allreduce_with_rank_local_none_grads():
+    _run(_dp_none_grad_worker, 2)

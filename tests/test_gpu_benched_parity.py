@@ -1,0 +1,229 @@
+"""GPU parity of the configuration bench.py actually times (tcgen05 scorer in fp16 / bf16 + kind::tf32 GEMMs, H = 256)
+against the REFERENCE's own fp32 training loop (golden trajectories step_hybrid_h256.npz / step_st_h256.npz, generated
+by tests/golden/make_golden.py from the unmodified reference at H = 256 with the Exp(1) noise tensors recorded).
+
+Stated bounds for reduced-precision operands (north_star: "stated looser bound for bf16 GEMM inputs"); every measured
+figure is also written to gpurun_out/parity_benched.json so the bounds can be audited:
+  * the conditional-gate branch decision of every epoch equals the reference's,
+  * per-epoch loss within LOSS_RTOL of the reference's,
+  * edge probabilities handed to the sampler within P_ATOL (abs) of the reference's, every epoch,
+  * sampled-set overlap with the reference's mask >= OVERLAP_MIN, every epoch (same injected noise),
+  * final parameters after 6 Adam epochs within PARAM_TOL * (1 + max|ref|).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+from types import SimpleNamespace
+
+from conftest import ROOT, FixtureBatch, load_golden, t
+
+pytestmark = pytest.mark.gpu
+
+# measured on B200 (gpurun_out/parity_benched.json, round 2) with ~3x head-room
+BOUNDS = {
+    "fp16": dict(LOSS_RTOL=5e-3, P_ATOL=1e-3, OVERLAP_MIN=0.995, PARAM_TOL=2e-3),
+    "bf16": dict(LOSS_RTOL=2e-2, P_ATOL=8e-3, OVERLAP_MIN=0.97, PARAM_TOL=4e-3),
+    "tf32": dict(LOSS_RTOL=1e-3, P_ATOL=1e-4, OVERLAP_MIN=0.999, PARAM_TOL=1e-3),
+}
+
+
+def make_args(dev, **kw):
+    a = dict(device=dev, mode="learned", hybrid_checkpoint=False, conditional=True, sparse_edge_mlp=True, t_init=0.7,
+             t_min=0.5, degree_bias_coef=0.3, reg1=True, reg2=True, regularizer1_coef=1.0, consist_reg_coef=0.5)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    from sgs_gnn_b200 import ops
+    before = ops.get_precision()
+    yield
+    ops.set_precision(**before)
+
+
+def _record(tag, rec):
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_benched.json")
+        data = json.load(open(path)) if os.path.isfile(path) else {}
+        data[tag] = rec
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("scorer", ["fp16", "bf16", "tf32"])
+@pytest.mark.parametrize("name,pipeline", [("step_hybrid_h256.npz", "hybrid"), ("step_st_h256.npz", "straight_through")])
+def test_benched_precision_trajectory_vs_reference(dev, name, pipeline, scorer, monkeypatch):
+    from sgs_gnn_b200 import _train_core, ops, sampling, training
+    from sgs_gnn_b200.model import GNNModel
+    if scorer == "tf32" and not ops.scorer_supports("tf32"):
+        pytest.skip("kind::tf32 scorer not built")
+    bd = BOUNDS[scorer]
+    z = load_golden(name)
+    b = FixtureBatch(z, dev)
+    f, c, h, q = b.x.size(1), int(b.y.max()) + 1, int(z["hidden"]), int(z["q"])
+    e = b.edge_index.size(1)
+    assert h == 256
+    ops.set_precision(gemm="tf32", scorer=scorer)
+    model = GNNModel(f, h, c, 0.0, "GCN")
+    model.load_state_dict({k[4:]: t(v) for k, v in z.items() if k.startswith("sd0.")})
+    model = model.to(dev)
+    opt_gnn = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-3)
+    opt_edge = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-3)
+    opt_all = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    scores = torch.softmax(t(z["prob"]), -1).to(dev)
+    monkeypatch.setattr(_train_core, "_softmax_prob", lambda prob: scores)
+    seen = []
+    inner = sampling.sample_edges
+
+    def spy(p, prob, q_, *a, **kw):
+        r = inner(p, prob, q_, *a, **kw)
+        seen.append((p.detach().clone(), r.sel.clone()))
+        return r
+    monkeypatch.setattr(sampling, "sample_edges", spy)
+    args = make_args(dev, pipeline=pipeline)
+    noises = t(z["noises"], dev)
+    epochs = noises.size(0)
+    ref_masks = np.unpackbits(z["ref_masks"], axis=1)[:, :e].astype(bool)
+    rec = {"loss_rel": [], "p_abs": [], "overlap": [], "branch_equal": []}
+    for ep in range(epochs):
+        sampling.clear_injected()
+        sampling.inject_noise([noises[ep, 0].contiguous(), noises[ep, 1].contiguous()])
+        loss, temp, n_cond, n_tot = training.train(args, ep, epochs, model, opt_gnn, opt_edge, opt_all,
+                                                   nn.CrossEntropyLoss(), [b], q=q, alternate_frequency=0)
+        want = float(z["losses"][ep])
+        p_got, sel = seen[-1]
+        mask = torch.zeros(e, dtype=torch.bool)
+        mask[sel.cpu().long()] = True
+        rec["loss_rel"].append(abs(loss - want) / max(1.0, abs(want)))
+        rec["p_abs"].append(float((p_got.cpu() - t(z["ref_p_full"][ep])).abs().max()))
+        rec["overlap"].append(float((mask & torch.from_numpy(ref_masks[ep])).sum()) / q)
+        rec["branch_equal"].append(bool(n_cond == int(z["learned_wins"][ep])))
+    sd1 = model.state_dict()
+    perr = {}
+    for k, v in z.items():
+        if k.startswith("sd1."):
+            got, want = sd1[k[4:]].cpu(), t(v)
+            perr[k[4:]] = float((got - want).abs().max()) / (1.0 + float(want.abs().max()))
+    rec["param_err_max"] = max(perr.values())
+    rec["param_err"] = perr
+    _record(f"{pipeline}/{scorer}", rec)
+    assert all(rec["branch_equal"]), rec
+    assert max(rec["loss_rel"]) < bd["LOSS_RTOL"], rec
+    assert max(rec["p_abs"]) < bd["P_ATOL"], rec
+    assert min(rec["overlap"]) >= bd["OVERLAP_MIN"], rec
+    assert rec["param_err_max"] < bd["PARAM_TOL"], rec
+
+
+def test_reddit_shape_sampler_bit_exact_vs_oracle(dev):
+    """The target of BASELINE.json, literally: at the Reddit shape (E = 114 615 892, q = 22 923 178) the sampled edge
+    set equals the oracle's topk(s / noise) on identical (p, prob, noise, S), bit for bit (ties: lowest edge id)."""
+    from oracle import extended as ox
+    from sgs_gnn_b200 import ops
+    e, q = 114_615_892, 22_923_178
+    g = torch.Generator(device=dev).manual_seed(2026)
+    p = torch.rand(e, generator=g, device=dev).pow_(2).mul_(0.98).add_(0.01)     # probabilities in (0.01, 0.99)
+    prob = torch.rand(e, generator=g, device=dev)
+    prob = torch.softmax(prob.mul_(3.0), 0)                                     # a degree-prior-like distribution
+    noise = ops.exponential(e, dev, seed=99)
+    pc, probc, noisec = p.cpu(), prob.cpu(), noise.cpu()
+    S = pc.sum().reshape(1)                                                     # torch's fp32 CPU reduction, injected
+    r = ops.sample_topq(p, prob, q, ops.SAMPLE_TRAIN, 0.3, noise=noise, S=S.to(dev), want_mask=True)
+    sel = r.sel.cpu().long()
+    mask = r.mask.view(torch.bool).cpu()
+    tau_gpu = r.tau
+    del p, prob, noise, r
+    torch.cuda.empty_cache()
+    # oracle (sampling.py:91-96 op for op; torch.multinomial == top-q of s / Exp(1))
+    s = ox.sampler_scores(pc, probc, 0.3, False, S=S[0])
+    keys = s / noisec
+    del s
+    want_sel, tau, n_gt = ox.topq_select(keys, q)
+    assert tau_gpu == tau
+    assert sel.numel() == q and torch.equal(sel, want_sel)
+    assert int(mask.sum()) == q and bool(mask[want_sel].all())
+    n_eq = int((keys == tau).sum())
+    _record("reddit_sampler", {"E": e, "q": q, "tau": tau, "n_greater": n_gt, "ties_at_tau": n_eq, "bit_exact": True})
+
+
+def _fake_multinomial(scores, noise_box):
+    """Stand-in for torch.multinomial inside the REFERENCE's training loop (the baseline draw, training_hybrid.py:47):
+    the same top-q of scores / Exp(1) the real one computes, with the golden noise tensor instead of a fresh draw."""
+    def multinomial(samples, num_samples, replacement=False, **kw):
+        noise = noise_box.pop(0)
+        return torch.topk(scores / noise, num_samples).indices
+    return multinomial
+
+
+def test_reference_training_loop_calls_dropin_modules(dev, monkeypatch):
+    """The UNMODIFIED reference training_hybrid.train (oracle/_ref or /root/reference) as the caller: its
+    `from sampling import *`, `from utils import ...` resolve to the drop-in modules, the model is the drop-in
+    GNNModel.  Exercises edge_prob_mlp(...) -> [E,1], .squeeze(), gumbel_softmax_sampling -> bool mask,
+    edge_index[:, mask], edge_probs_full[mask] (torch's index backward into the fused scorer backward over all E
+    edges), model(batch, int64 [2,q], weights), calculate_f1, consistency_loss.  3 epochs match the golden losses."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference modules not staged (run oracle/make_ref.py in the builder container)")
+    from sgs_gnn_b200 import sampling
+    from sgs_gnn_b200.model import GNNModel
+    ns = ref_loader.load_callers(os.path.join(ROOT, "sgs_gnn_b200", "dropin"))
+    assert ns.training_hybrid.gumbel_softmax_sampling is sampling.gumbel_softmax_sampling
+    z = load_golden("step_hybrid.npz")
+    b = FixtureBatch(z, dev)
+    f, c, h, q = b.x.size(1), int(b.y.max()) + 1, int(z["hidden"]), int(z["q"])
+    model = GNNModel(f, h, c, 0.0, "GCN")
+    model.load_state_dict({k[4:]: t(v) for k, v in z.items() if k.startswith("sd0.")})
+    model = model.to(dev)
+    opt_gnn = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-3)
+    opt_edge = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-3)
+    opt_all = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    scores = torch.softmax(t(z["prob"]), -1).to(dev)
+    noises = t(z["noises"], dev)
+    args = make_args(dev)
+    box = []
+    monkeypatch.setattr(torch, "multinomial", _fake_multinomial(scores, box))
+    for ep in range(3):
+        box[:] = [noises[ep, 0]]
+        sampling.clear_injected()
+        sampling.inject_noise([noises[ep, 1].contiguous()])
+        loss, temp, n_cond, n_tot = ns.training_hybrid.train(args, ep, 6, model, opt_gnn, opt_edge, opt_all,
+                                                            nn.CrossEntropyLoss(), [b], q=q, alternate_frequency=0)
+        assert n_cond == int(z["learned_wins"][ep]), f"epoch {ep}: branch differs from the reference"
+        assert abs(loss - float(z["losses"][ep])) < 2e-4 * max(1.0, abs(float(z["losses"][ep]))), (ep, loss)
+
+
+def test_reference_evaluate_calls_dropin_modules(dev):
+    """The unmodified reference evaluate.ensemble_evaluate / evaluate as the caller of the drop-in model + sampler
+    (evaluate.py:84-88: [E,1] output, istest sampling, weights (p*st)[mask].clamp(0,1))."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference modules not staged")
+    from sgs_gnn_b200 import sampling
+    from sgs_gnn_b200.model import GNNModel
+    ns = ref_loader.load_callers(os.path.join(ROOT, "sgs_gnn_b200", "dropin"))
+    z = load_golden("eval_small.npz")
+    b = FixtureBatch(z, dev)
+    b.val_mask, b.test_mask = t(z["val_mask"], dev), t(z["test_mask"], dev)
+    f, c, h = b.x.size(1), int(b.y.max()) + 1, int(z["hidden"])
+    model = GNNModel(f, h, c, 0.3, "GCN")
+    model.load_state_dict({k[3:]: t(v) for k, v in z.items() if k.startswith("sd.")})
+    model = model.to(dev)
+    args = SimpleNamespace(degree_bias_coef=0.3, num_samples_eval=int(z["members"]))
+    n_masks = [int(b.train_mask.sum()), int(b.val_mask.sum()), int(b.test_mask.sum())]
+    sampling.clear_injected()
+    sampling.inject_noise([row.contiguous() for row in t(z["noises"], dev)])
+    f1 = ns.evaluate.ensemble_evaluate(args, model, [b], dev, q=int(z["q"]), mode="learned")
+    for got, want, cnt in zip(f1, z["f1_ensemble"], n_masks):
+        assert abs(got - float(want)) <= 1.0 / cnt + 1e-9, (f1, z["f1_ensemble"])
+    sampling.clear_injected()
+    sampling.inject_noise([t(z["noise_one"], dev)])
+    f1 = ns.evaluate.evaluate(args, model, [b], dev, q=int(z["q"]), mode="learned")
+    for got, want, cnt in zip(f1, z["f1_single"], n_masks):
+        assert abs(got - float(want)) <= 1.0 / cnt + 1e-9, (f1, z["f1_single"])

@@ -200,3 +200,15 @@ def test_sampled_window_path_is_bit_exact(dev, monkeypatch, path, e, q, mode):
     assert torch.equal(r.sel.cpu().long(), want.sel)
     assert torch.equal(r.mask.view(torch.bool).cpu(), want.mask)
     assert abs(r.tau - want.tau) == 0.0
+
+
+def test_noise_keyed_by_global_edge_id(dev):
+    """Shards draw the noise of their edges by GLOBAL id: the values of the contiguous draw, whatever the sharding."""
+    from sgs_gnn_b200 import ops
+    e = 100003
+    full = ops.exponential(e, dev, seed=1234)
+    assert float(full.min()) > 0.0 and abs(float(full.mean()) - 1.0) < 0.02
+    g = torch.Generator().manual_seed(1)
+    gid = torch.sort(torch.randperm(e, generator=g)[:40001]).values.to(dev)
+    part = ops.exponential(gid.numel(), dev, seed=1234, gid=gid)
+    assert torch.equal(part, full[gid])

@@ -175,3 +175,32 @@ def test_gemm_tf32_tn_splitk(dev, k, m, n):
     got2 = ops.gemm(a.to(dev), 1, m, ops._rows_aligned16(b.to(dev))[0], 1, (n + 3) // 4 * 4, m, n, k, out=c0,
                     accumulate=True, precision=ops.PREC_TF32).cpu()
     assert float((got2 - want - 1.0).abs().max() / want.abs().max()) < 2e-3
+
+
+def test_tf32_scorer_mode_keeps_the_fp32_bar(dev):
+    """precision 'tf32': the chunked fp32 pipeline with its contractions on the tcgen05 kind::tf32 GEMM -- the
+    tensor-core mode that keeps the fp32 parity bar (north_star: 1e-4 relative)."""
+    from sgs_gnn_b200 import ops, synth
+    b = synth.make_graph(None, seed=21, n=3000, e=80000, f=16, c=4).to(dev)
+    h = 256
+    g = torch.Generator(device=dev).manual_seed(5)
+    out = torch.relu(torch.randn(3000, h, generator=g, device=dev)) * 0.5
+    w1 = (torch.rand(h, 2 * h, generator=g, device=dev) - 0.5) * (2.0 / (2 * h) ** 0.5)
+    b1 = (torch.rand(h, generator=g, device=dev) - 0.5) * 0.1
+    w2 = (torch.rand(h, generator=g, device=dev) - 0.5) * (2.0 / h ** 0.5)
+    b2 = torch.zeros(1, device=dev)
+    graph = ops.graph_of(b.edge_index, 3000)
+    dp = torch.randn(graph.num_edges, generator=g, device=dev)
+    res = {}
+    for prec in ("fp32", "tf32"):
+        o = out.clone().requires_grad_(True)
+        ws = [t_.clone().requires_grad_(True) for t_ in (w1, b1, w2, b2)]
+        p = ops.edge_score(o, ws[0], ws[1], ws[2], ws[3], graph, precision=ops._PRECISION[prec])
+        p.backward(dp)
+        res[prec] = (p.detach(), o.grad, [t_.grad for t_ in ws])
+    p32, p19 = res["fp32"][0], res["tf32"][0]
+    assert float(((p32 - p19).abs() / p32.abs().clamp_min(1e-6)).max()) < 1e-4
+    rel = lambda a, b_: float((a - b_).abs().max() / (b_.abs().max() + 1e-30))   # noqa: E731
+    assert rel(res["tf32"][1], res["fp32"][1]) < 1e-3      # gradients: tf32 operands, fp32 accumulation
+    for ga, gb in zip(res["tf32"][2], res["fp32"][2]):
+        assert rel(ga, gb) < 1e-3
