@@ -326,7 +326,7 @@ def run_gpu_arm(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ops.set_precision(gemm=a.gemm_precision, scorer=a.precision)
+    ops.set_precision(gemm=a.gemm_precision, scorer=a.precision, gather=a.gather_precision)
     _lib.lib()
 
     shard = world > 1 and a.parallel == "shard"
@@ -581,6 +581,7 @@ def run_gpu_arm(a):
                        "gate": ("forced learned-wins: both forwards + gate are computed, then every step runs the full "
                                 "learned branch incl. the scorer backward" if a.gate == "learned" else "natural"),
                        "scorer_precision": a.precision, "gemm_precision": a.gemm_precision,
+                       "gather_precision": a.gather_precision,
                        "parallelism": "single" if world == 1 else (
                            f"shard{world}: one graph, edges sharded by destination-node range; distributed radix "
                            "top-q (digit-histogram all-reduce), slab all-gather / reduce-scatter, partial weight-grad "
@@ -607,9 +608,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E of the GPU workload (debug only)")
     ap.add_argument("--cpu-scale", type=float, default=1.0 / 128, help="bounded CPU sample: N, E scaled by this")
     ap.add_argument("--precision", default=os.environ.get("SGS_SCORER_PRECISION", "fp16"),
-                    choices=["fp32", "bf16", "fp16"])
+                    choices=["fp32", "bf16", "fp16", "tf32"])
     ap.add_argument("--gemm-precision", default=os.environ.get("SGS_GEMM_PRECISION", "tf32"),
                     choices=["fp32", "bf16", "fp16", "tf32"])
+    ap.add_argument("--gather-precision", default=os.environ.get("SGS_GATHER_PRECISION", "fp16"),
+                    choices=["fp32", "fp16"], help="storage of the rows the D >= 64 SpMM / SDDMM gather")
     ap.add_argument("--drop-rate", type=float, default=0.3)
     ap.add_argument("--parallel", default=os.environ.get("SGS_PARALLEL", "shard"), choices=["shard", "dp"],
                     help="N > 1: shard ONE graph by destination range (strong scaling) or one graph per rank (weak)")

@@ -116,6 +116,22 @@ int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what,
 /* ------------------------------------------------------------------------------------------
  * K3c backward helpers (autograd of GCNConv, training_hybrid.py:135)
  * ---------------------------------------------------------------------------------------- */
+/* fp16 gather tables (fast mode of the D = 256 SpMM / SDDMM: half the gathered bytes, table L2-resident).
+ * sgs_table_f16: out16[N*D] = fp16(in * S), S a power of two -- 1 when scaled == 0 (activations), else chosen from
+ * max|in| so that it maps into [8192, 16384) (gradient tables).  tscale: device float[4] = {S, 1/S, scratch, -}.
+ * sgs_spmm_h16 / sgs_gcn_edge_grad_h16: as sgs_spmm / sgs_gcn_edge_grad with h given as such a table; fp32
+ * accumulation, 1/S applied in the epilogue.  D % 8 == 0, D <= 512. */
+int32_t sgs_table_f16(const float* in, int64_t N, int64_t D, int32_t scaled, void* out16, float* tscale,
+                      sgs_stream_t stream);
+int32_t sgs_spmm_h16(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                     const float* dis, const float* loopw, const void* h16, const float* tscale, int64_t N, int64_t D,
+                     const float* bias, float* out, int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream);
+int32_t sgs_gcn_edge_grad_h16(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
+                              const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
+                              const int32_t* perm_src, const int32_t* src, const int32_t* dst, const float* G,
+                              const void* h16, const float* tscale, const float* dis, const float* deg,
+                              const float* loopw, int64_t M, int64_t N, int64_t D, float* tmp_g, float* tmp_t,
+                              float* tmp_a, float* dw, int32_t accumulate, sgs_stream_t stream);
 /* gin = gout * (out > 0) * scale      (ReLU + inverted-dropout backward; out is the saved
  * post-activation output, scale = 1/(1-p)) */
 int32_t sgs_act_bwd(const float* gout, const float* out, int64_t n, float scale, float* gin,
@@ -144,6 +160,10 @@ int32_t sgs_gcn_edge_grad_partial(const int32_t* rowptr_dst, const int32_t* perm
 int32_t sgs_gcn_edge_grad_final(const int32_t* src, const int32_t* dst, const float* tmp_g,
                                 const float* tmp_a, const float* dis, const float* deg, int64_t M,
                                 float* dw, int32_t accumulate, sgs_stream_t stream);
+
+/* out[i] = in[i] rounded to the nearest tf32 value (10 mantissa bits; cvt.rna).  kind::tf32 MMAs truncate their
+ * fp32 operands; rounding them first makes the error unbiased (in == out allowed). */
+int32_t sgs_round_tf32(const float* in, int64_t n, float* out, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 dense contraction  C[M,N] (+)= A[M,K] . B[N,K]^T with arbitrary element strides
@@ -180,6 +200,23 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
                            uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
                            float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream);
+
+/* Gate bits: what the hybrid pipeline keeps from the forward over ALL edges so that the backward over the q sampled
+ * ones (training_hybrid.py:86 `edge_probs_full[mask]` -> autograd) needs no recompute of the hidden layer.
+ * gates[e, j / 8] bit (j % 8) = [hidden pre-activation j of edge e > 0] * [dropout keeps it]; H / 8 bytes per edge,
+ * indexed by the position in the forward's edge list.  sgs_edge_score_gate_bytes returns 0 when the mode cannot
+ * produce them (then pass gates = NULL and the backward recomputes).  The backward's `gates` is the forward's array
+ * over the SAME (src, dst, ids = NULL) list; its own `ids` pick the rows. */
+size_t sgs_edge_score_gate_bytes(int64_t n, int64_t H, int32_t precision);
+int32_t sgs_edge_score_fwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
+                                 const float* b2, float p_drop, uint64_t seed, float* p, void* gates, void* ws,
+                                 size_t ws_bytes, int32_t precision, sgs_stream_t stream);
+int32_t sgs_edge_score_bwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
+                                 const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
+                                 const void* gates, float* d_out, float* dW1, float* db1, float* dw2, float* db2,
+                                 void* ws, size_t ws_bytes, int32_t precision, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 sampler  (sampling.py:91-155 gumbel_softmax_sampling + the compaction at

@@ -34,16 +34,24 @@ SIGNATURES = {
     "sgs_gcn_norm": (I32, [P, P, P, P, I64, I64, P, P, P, P, P]),
     "sgs_gcn_norm_apply": (I32, [P, P, P, P, P, I64, I64, P, P]),
     "sgs_spmm": (I32, [P, P, P, P, P, P, P, I64, I64, P, P, I32, F32, U64, P]),
+    "sgs_table_f16": (I32, [P, I64, I64, I32, P, P, P]),
+    "sgs_spmm_h16": (I32, [P, P, P, P, P, P, P, P, I64, I64, P, P, I32, F32, U64, P]),
+    "sgs_gcn_edge_grad_h16": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, P]),
     "sgs_act_bwd": (I32, [P, P, I64, F32, P, P]),
     "sgs_colsum": (I32, [P, I64, I64, P, P]),
     "sgs_gcn_edge_grad": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, P]),
     "sgs_gcn_edge_grad_partial": (I32, [P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P]),
     "sgs_gcn_edge_grad_final": (I32, [P, P, P, P, P, P, I64, P, I32, P]),
+    "sgs_round_tf32": (I32, [P, I64, P, P]),
     "sgs_gemm": (I32, [P, I64, I64, P, I64, I64, P, I64, I64, I64, I64, I32, I32, P]),
     "sgs_edge_score_workspace_bytes": (SZ, [I64, I64, I64, I32, I32]),
     "sgs_edge_score_fwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, SZ, I32, P]),
     "sgs_edge_score_bwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, P, P, P, P, P, SZ,
                                  I32, P]),
+    "sgs_edge_score_gate_bytes": (SZ, [I64, I64, I32]),
+    "sgs_edge_score_fwd_gates": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, SZ, I32, P]),
+    "sgs_edge_score_bwd_gates": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, P, P, P, P, P, P,
+                                       SZ, I32, P]),
     "sgs_sum_f32": (I32, [P, I64, P, P, SZ, P]),
     "sgs_softmax_f32": (I32, [P, I64, P, P, SZ, P]),
     "sgs_exponential_f32": (I32, [P, I64, U64, P]),

@@ -11,15 +11,16 @@ namespace sgs {
 
 int32_t edge_score_fwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                           const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                          const float* b2, float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes,
-                          int32_t precision, cudaStream_t st);
+                          const float* b2, float p_drop, uint64_t seed, float* p, uint32_t* mask, void* ws,
+                          size_t ws_bytes, int32_t precision, cudaStream_t st);
+bool edge_score_gate_bits_supported(int64_t H, int32_t precision);
 size_t edge_score_tc_workspace_bytes(int64_t n, int64_t N, int64_t H);
 size_t edge_score_bwd_tc_workspace_bytes(int64_t n, int64_t N, int64_t H);
 int32_t edge_score_bwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                           const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
                           float p_drop, uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
-                          float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int32_t precision,
-                          cudaStream_t st);
+                          float* db1, float* dw2, float* db2, const uint32_t* mask, void* ws, size_t ws_bytes,
+                          int32_t precision, cudaStream_t st);
 static inline bool tc_bwd_supported(int32_t precision, int64_t H) {
   return (precision == SGS_PREC_BF16 || precision == SGS_PREC_FP16) && (H == 128 || H == 256);
 }
@@ -30,13 +31,27 @@ constexpr int64_t kMaxChunk = 131072;
 constexpr int64_t kMaxChunkTf32 = 32768;   // F (64 MB at H = 256) + Z (32 MB) of a chunk fit the 126 MB L2
 static inline bool is_16bit(int32_t precision) { return precision == SGS_PREC_BF16 || precision == SGS_PREC_FP16; }
 
-// Wt[c, r] = W[r, c]   (W [R, C] row-major; tiny: H x 2H)
-__global__ void transpose_small_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ Wt) {
+// Wr = rna_tf32(W), Wt[c, r] = rna_tf32(W[r, c])   (W [R, C] row-major; tiny: H x 2H)
+__global__ void round_transpose_small_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ Wr,
+                                             float* __restrict__ Wt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < R * C) Wt[(int64_t)(i % C) * R + i / C] = W[i];
+  if (i < R * C) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(W[i]));
+    Wr[i] = __uint_as_float(r);
+    if (Wt) Wt[(int64_t)(i % C) * R + i / C] = __uint_as_float(r);
+  }
 }
 
-// F[i, c] = x*y, F[i, H+c] = x-y   (one warp per edge, float4 columns)
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// F[i, c] = x*y, F[i, H+c] = x-y   (one warp per edge, float4 columns); RND: values rounded to the nearest tf32
+// (operands of the truncating kind::tf32 MMA, see gemm.cu)
+template <bool RND>
 __global__ void __launch_bounds__(kThreads)
 edge_feat_kernel(const float* __restrict__ out, int H, const int32_t* __restrict__ src,
                  const int32_t* __restrict__ dst, const int32_t* __restrict__ ids, int64_t e0, int64_t n,
@@ -52,8 +67,14 @@ edge_feat_kernel(const float* __restrict__ out, int H, const int32_t* __restrict
     for (int c = lane * 4; c < H; c += 128) {
       const float4 a = *reinterpret_cast<const float4*>(x + c);
       const float4 b = *reinterpret_cast<const float4*>(y + c);
-      *reinterpret_cast<float4*>(f + c) = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
-      *reinterpret_cast<float4*>(f + H + c) = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+      float4 pr = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+      float4 df = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+      if (RND) {
+        pr = make_float4(rna_tf32(pr.x), rna_tf32(pr.y), rna_tf32(pr.z), rna_tf32(pr.w));
+        df = make_float4(rna_tf32(df.x), rna_tf32(df.y), rna_tf32(df.z), rna_tf32(df.w));
+      }
+      *reinterpret_cast<float4*>(f + c) = pr;
+      *reinterpret_cast<float4*>(f + H + c) = df;
     }
   }
 }
@@ -61,7 +82,7 @@ edge_feat_kernel(const float* __restrict__ out, int H, const int32_t* __restrict
 // hidden = dropout(relu(Z + b1)); z = w2.hidden + b2; p = sigmoid(z)
 // BWD: also dA = dz * w2 * keep_scale * [Z + b1 > 0] written over Z, and the small parameter
 // gradients reduced per block.
-template <bool BWD>
+template <bool BWD, bool RND = false>
 __global__ void __launch_bounds__(kThreads)
 edge_hidden_kernel(float* __restrict__ Z, int H, const float* __restrict__ b1, const float* __restrict__ w2,
                    const float* __restrict__ b2, const int32_t* __restrict__ ids, int64_t e0, int64_t n,
@@ -130,6 +151,10 @@ edge_hidden_kernel(float* __restrict__ Z, int H, const float* __restrict__ b1, c
             da[t] = on ? dz * wv[t] * scale : 0.f;
             acc_w2[k][t] += on ? dz * (pre[t] * scale) : 0.f;
             acc_b1[k][t] += da[t];
+          }
+          if (RND) {   // dA is the operand of two more kind::tf32 GEMMs
+#pragma unroll
+            for (int t = 0; t < 4; ++t) da[t] = rna_tf32(da[t]);
           }
           *reinterpret_cast<float4*>(zr + c) = make_float4(da[0], da[1], da[2], da[3]);
         }
@@ -213,21 +238,37 @@ size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t N, int64_t H, int32_t p
   if (backward && tc_bwd_supported(precision, H)) return edge_score_bwd_tc_workspace_bytes(n, N, H);
   const int64_t cap = precision == SGS_PREC_TF32 ? kMaxChunkTf32 : kMaxChunk;
   const int64_t chunk = n < cap ? n : cap;
-  return (size_t)chunk * per_edge_bytes(H, backward) + 256 + (size_t)2 * H * H * sizeof(float) + 256;
+  return (size_t)chunk * per_edge_bytes(H, backward) + 256 + 2 * ((size_t)2 * H * H * sizeof(float) + 256);
+}
+
+size_t sgs_edge_score_gate_bytes(int64_t n, int64_t H, int32_t precision) {
+  if (n <= 0 || !edge_score_gate_bits_supported(H, precision)) return 0;
+  return (size_t)n * (size_t)(H / 8);
 }
 
 int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                            const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
                            const float* b2, float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream) {
+  return sgs_edge_score_fwd_gates(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, nullptr, ws, ws_bytes,
+                                  precision, stream);
+}
+
+int32_t sgs_edge_score_fwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
+                                 const float* b2, float p_drop, uint64_t seed, float* p, void* gates, void* ws,
+                                 size_t ws_bytes, int32_t precision, sgs_stream_t stream) {
   SGS_CHECK_ARG(n >= 0 && N > 0 && H > 0 && H % 4 == 0, "bad sizes (H must be a multiple of 4)");
   if (n == 0) return SGS_OK;
   SGS_CHECK_ARG(out && src && dst && W1 && b1 && w2 && b2 && p && ws, "null pointer");
   SGS_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "p_drop must be in [0,1)");
+  SGS_CHECK_ARG(!gates || edge_score_gate_bits_supported(H, precision),
+                "gate bits need H = 256 and a 16-bit tensor-core precision (see sgs_edge_score_gate_bytes)");
+  SGS_CHECK_ARG(((uintptr_t)gates & 15) == 0, "gates must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (is_16bit(precision))
-    return edge_score_fwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, ws, ws_bytes,
-                             precision, st);
+    return edge_score_fwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p,
+                             reinterpret_cast<uint32_t*>(gates), ws, ws_bytes, precision, st);
   SGS_CHECK_ARG(precision == SGS_PREC_FP32 || precision == SGS_PREC_TF32, "unknown precision");
   const int32_t gprec = precision == SGS_PREC_TF32 ? SGS_PREC_TF32 : SGS_PREC_FP32;
   const size_t pe = per_edge_bytes(H, 0);
@@ -235,13 +276,31 @@ int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t
   if (chunk > (gprec == SGS_PREC_TF32 ? kMaxChunkTf32 : kMaxChunk)) chunk = gprec == SGS_PREC_TF32 ? kMaxChunkTf32 : kMaxChunk;
   if (chunk > n) chunk = n;
   if (chunk < 1) { set_error("sgs_edge_score_fwd: workspace too small"); return SGS_E_WORKSPACE; }
+  const size_t wt_bytes = (size_t)2 * H * H * sizeof(float) + 256;
+  if (gprec == SGS_PREC_TF32 && ws_bytes < 256 + pe + wt_bytes) {
+    set_error("sgs_edge_score_fwd: workspace too small");
+    return SGS_E_WORKSPACE;
+  }
+  if (gprec == SGS_PREC_TF32) {
+    const int64_t room = (int64_t)((ws_bytes - 256 - wt_bytes) / pe);
+    if (chunk > room) chunk = room;
+  }
   float* F = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   float* Z = F + chunk * 2 * H;
+  const float* W1g = W1;
+  if (gprec == SGS_PREC_TF32) {   // weights rounded to the nearest tf32 once per call
+    float* W1r = (float*)(((uintptr_t)(Z + chunk * H) + 255) & ~(uintptr_t)255);
+    round_transpose_small_kernel<<<(unsigned)ceil_div(2 * H * H, 256), 256, 0, st>>>(W1, (int)H, (int)(2 * H), W1r,
+                                                                                    nullptr);
+    SGS_LAUNCH_CHECK();
+    W1g = W1r;
+  }
   for (int64_t e0 = 0; e0 < n; e0 += chunk) {
     const int64_t m = (n - e0 < chunk) ? n - e0 : chunk;
-    edge_feat_kernel<<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
+    if (gprec == SGS_PREC_TF32) edge_feat_kernel<true><<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
+    else edge_feat_kernel<false><<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
     SGS_LAUNCH_CHECK();
-    int32_t rc = sgs_gemm(F, 2 * H, 1, W1, 2 * H, 1, Z, H, m, H, 2 * H, 0, gprec, stream);
+    int32_t rc = sgs_gemm(F, 2 * H, 1, W1g, 2 * H, 1, Z, H, m, H, 2 * H, 0, gprec, stream);
     if (rc) return rc;
     edge_hidden_kernel<false><<<edge_grid(m), kThreads, 0, st>>>(Z, (int)H, b1, w2, b2, ids, e0, m, p_drop, seed,
                                                                  p + e0, nullptr, nullptr, nullptr, nullptr);
@@ -255,7 +314,18 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
                            const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
                            float* d_out, float* dW1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream) {
+  return sgs_edge_score_bwd_gates(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p_fwd, dp, nullptr, d_out,
+                                  dW1, db1, dw2, db2, ws, ws_bytes, precision, stream);
+}
+
+int32_t sgs_edge_score_bwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
+                                 const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
+                                 const void* gates, float* d_out, float* dW1, float* db1, float* dw2, float* db2,
+                                 void* ws, size_t ws_bytes, int32_t precision, sgs_stream_t stream) {
   SGS_CHECK_ARG(n >= 0 && N > 0 && H > 0 && H % 4 == 0, "bad sizes (H must be a multiple of 4)");
+  SGS_CHECK_ARG(!gates || (edge_score_gate_bits_supported(H, precision) && ((uintptr_t)gates & 15) == 0),
+                "gate bits need H = 256, a 16-bit tensor-core precision and 16-byte alignment");
   if (n == 0) return SGS_OK;
   SGS_CHECK_ARG(out && src && dst && W1 && b1 && w2 && b2 && dp && d_out && dW1 && db1 && dw2 && db2 && ws,
                 "null pointer");
@@ -266,14 +336,14 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
   if (tc_bwd_supported(precision, H)) {
     SGS_CHECK_ARG(p_fwd != nullptr, "tensor-core backward needs the forward probabilities p_fwd");
     return edge_score_bwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, dw2,
-                             db2, ws, ws_bytes, precision, st);
+                             db2, reinterpret_cast<const uint32_t*>(gates), ws, ws_bytes, precision, st);
   }
   SGS_CHECK_ARG(precision == SGS_PREC_FP32 || precision == SGS_PREC_TF32 || is_16bit(precision), "unknown precision");
   // kind::tf32 needs 16-byte aligned rows; 16-bit modes at widths the fused kernels do not cover use fp32
   const bool tf32 = precision == SGS_PREC_TF32;
   const int32_t gprec = tf32 ? SGS_PREC_TF32 : SGS_PREC_FP32;
   const size_t pe = per_edge_bytes(H, 1);
-  const size_t wt_bytes = (size_t)2 * H * H * sizeof(float) + 256;
+  const size_t wt_bytes = 2 * ((size_t)2 * H * H * sizeof(float) + 256);
   int64_t chunk = (int64_t)((ws_bytes > 256 + wt_bytes ? ws_bytes - 256 - wt_bytes : 0) / pe);
   if (chunk > (tf32 ? kMaxChunkTf32 : kMaxChunk)) chunk = tf32 ? kMaxChunkTf32 : kMaxChunk;
   if (chunk > n) chunk = n;
@@ -282,19 +352,28 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
   float* Z = F + chunk * 2 * H;   // becomes dA
   float* dF = Z + chunk * H;
   float* W1t = (float*)(((uintptr_t)(dF + chunk * 2 * H) + 255) & ~(uintptr_t)255);   // [2H, H]
+  float* W1r = (float*)(((uintptr_t)(W1t + 2 * H * H) + 255) & ~(uintptr_t)255);      // [H, 2H]
+  const float* W1g = W1;
   if (tf32) {
-    transpose_small_kernel<<<(unsigned)ceil_div(2 * H * H, 256), 256, 0, st>>>(W1, (int)H, (int)(2 * H), W1t);
+    round_transpose_small_kernel<<<(unsigned)ceil_div(2 * H * H, 256), 256, 0, st>>>(W1, (int)H, (int)(2 * H), W1r,
+                                                                                    W1t);
     SGS_LAUNCH_CHECK();
+    W1g = W1r;
   }
   const size_t shmem = (size_t)(2 * H + 1) * sizeof(float);
   for (int64_t e0 = 0; e0 < n; e0 += chunk) {
     const int64_t m = (n - e0 < chunk) ? n - e0 : chunk;
-    edge_feat_kernel<<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
+    if (tf32) edge_feat_kernel<true><<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
+    else edge_feat_kernel<false><<<edge_grid(m), kThreads, 0, st>>>(out, (int)H, src, dst, ids, e0, m, F);
     SGS_LAUNCH_CHECK();
-    int32_t rc = sgs_gemm(F, 2 * H, 1, W1, 2 * H, 1, Z, H, m, H, 2 * H, 0, gprec, stream);
+    int32_t rc = sgs_gemm(F, 2 * H, 1, W1g, 2 * H, 1, Z, H, m, H, 2 * H, 0, gprec, stream);
     if (rc) return rc;
-    edge_hidden_kernel<true><<<edge_grid(m), kThreads, shmem, st>>>(Z, (int)H, b1, w2, b2, ids, e0, m, p_drop, seed,
-                                                                    nullptr, dp + e0, dw2, db1, db2);
+    if (tf32)
+      edge_hidden_kernel<true, true><<<edge_grid(m), kThreads, shmem, st>>>(Z, (int)H, b1, w2, b2, ids, e0, m, p_drop,
+                                                                            seed, nullptr, dp + e0, dw2, db1, db2);
+    else
+      edge_hidden_kernel<true><<<edge_grid(m), kThreads, shmem, st>>>(Z, (int)H, b1, w2, b2, ids, e0, m, p_drop, seed,
+                                                                      nullptr, dp + e0, dw2, db1, db2);
     SGS_LAUNCH_CHECK();
     // dF[m,2H] = dA[m,H] . W1[H,2H]
     if (tf32) rc = sgs_gemm(Z, H, 1, W1t, H, 1, dF, 2 * H, m, 2 * H, H, 0, SGS_PREC_TF32, stream);   // NT vs W1^T

@@ -1,6 +1,8 @@
 // K3: gcn_norm, CSR SpMM (forward, and backward via the by-source CSR), activation backward,
 // bias gradient and the edge-weight gradient (SDDMM + per-node sums).
 // All segment reductions are atomic-free: one warp owns one CSR row.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sgs {
@@ -217,6 +219,183 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// 16-bit gather tables.  The D = 256 SpMM / SDDMM are bound by the row gathers (ncu r01: 1 KB per edge from a 239 MB
+// fp32 table, L2 hit rate 50 %, DRAM at 58 %).  With the table in fp16 -- 119 MB at Reddit scale, i.e. L2-resident --
+// a gathered row is 512 B and (nearly) never leaves L2.  Accumulation stays fp32; the table carries a power-of-two
+// scale (gradient tables: max |v| -> [8192, 16384)) that is divided out in the epilogue.
+// ---------------------------------------------------------------------------------------
+__global__ void table_absmax_kernel(const float* __restrict__ x, int64_t n4, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+// scale[0] = S (power of two), scale[1] = 1 / S; S = 1 when no absmax is given (activations: |v| << 65504)
+__global__ void table_scale_kernel(const float* __restrict__ absmax, float* __restrict__ scale) {
+  float S = 1.0f;
+  if (absmax) {
+    const float m = absmax[0];
+    if (m > 0.f && !isinf(m) && !isnan(m)) S = exp2f(floorf(log2f(16384.0f / m)));
+  }
+  scale[0] = S;
+  scale[1] = 1.0f / S;
+}
+__global__ void table_convert_kernel(const float* __restrict__ in, int64_t n8, const float* __restrict__ scale,
+                                     uint4* __restrict__ outp) {
+  const float S = scale[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(in) + 2 * i);
+    const float4 b = ld_stream_f4(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+    auto pk = [&](float x, float y) {
+      const __half2 v = __floats2half2_rn(fminf(fmaxf(x * S, -65504.f), 65504.f), fminf(fmaxf(y * S, -65504.f), 65504.f));
+      return *reinterpret_cast<const uint32_t*>(&v);
+    };
+    outp[i] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), pk(b.z, b.w));
+  }
+}
+
+__device__ __forceinline__ void h8_to_float(const uint4& u, float* f) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+  const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// SpMM over an fp16 table [N, D], D % 8 == 0, D <= 256 * K: lane owns the 8 columns 8 * (k * 32 + lane).
+template <int K>
+struct SpmmRowH {
+  float acc[K][8];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int v = 0; v < 8; ++v) acc[k][v] = 0.f;
+  }
+  __device__ __forceinline__ void gather(const int32_t* __restrict__ nbr, const float* __restrict__ what,
+                                         const __half* __restrict__ h, int D, int lane, int beg, int end, int first,
+                                         int nstep) {
+    for (int base = beg + 32 * first; base < end; base += 32 * nstep) {
+      int my_n = 0;
+      float my_w = 0.f;
+      if (base + lane < end) {
+        my_n = nbr[base + lane];
+        my_w = what[base + lane];
+      }
+      const int cnt = min(32, end - base);
+#pragma unroll 8
+      for (int j = 0; j < cnt; ++j) {
+        const int n = __shfl_sync(0xffffffffu, my_n, j);
+        const float wv = __shfl_sync(0xffffffffu, my_w, j);
+        const __half* hp = h + (int64_t)n * D;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = (k * 32 + lane) * 8;
+          if (c < D) {
+            float x[8];
+            h8_to_float(*reinterpret_cast<const uint4*>(hp + c), x);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[k][t] = fmaf(wv, x[t], acc[k][t]);
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(int64_t row, const float* __restrict__ dis, const float* __restrict__ loopw,
+                                         const __half* __restrict__ h, int D, int lane, float inv_scale,
+                                         const float* __restrict__ bias, float* __restrict__ out, int flags,
+                                         float scale, uint32_t thr, uint64_t seed) {
+    float selfw = 0.f;
+    if (dis) {
+      const float d = dis[row];
+      selfw = d * d * (loopw ? loopw[row] : 1.0f);
+    }
+    const __half* hr = h + row * D;
+    float* orow = out + row * D;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        float v[8], self[8];
+        if (dis) h8_to_float(*reinterpret_cast<const uint4*>(hr + c), self);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          v[t] = acc[k][t];
+          if (dis) v[t] = fmaf(selfw, self[t], v[t]);
+          v[t] *= inv_scale;
+          if (flags & SGS_SPMM_ADD_ROOT) v[t] += orow[c + t];
+          if (bias) v[t] += bias[c + t];
+          if (flags & SGS_SPMM_RELU) v[t] = fmaxf(v[t], 0.f);
+        }
+        if (flags & SGS_SPMM_DROPOUT) {
+#pragma unroll
+          for (int g4 = 0; g4 < 2; ++g4) {
+            const uint64_t bits = dropout_bits(seed, (uint64_t)row, (uint32_t)((c >> 2) + g4));
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[4 * g4 + t] = dropout_keep(bits, t, thr) ? v[4 * g4 + t] * scale : 0.f;
+          }
+        }
+        if (flags & SGS_SPMM_ACCUM) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] += orow[c + t];
+        }
+        *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(orow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ what,
+                const float* __restrict__ dis, const float* __restrict__ loopw, const __half* __restrict__ h,
+                const float* __restrict__ tscale, int64_t N, int D, const float* __restrict__ bias,
+                float* __restrict__ out, int flags, float p_drop, uint64_t seed, const int32_t* __restrict__ order) {
+  __shared__ float red[kWarpsPerBlock - 1][32 * 8 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t thr = dropout_threshold(p_drop);
+  const float scale = (flags & SGS_SPMM_DROPOUT) ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const float inv_scale = tscale[1];
+  const int n_heavy = order ? order[N] : 0;
+  SpmmRowH<K> r;
+  for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
+    const int64_t row = order[hidx];
+    r.clear();
+    r.gather(nbr, what, h, D, lane, rowptr[row], rowptr[row + 1], warp, kWarpsPerBlock);
+    if (warp > 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) red[warp - 1][(k * 32 + lane) * 8 + v] = r.acc[k][v];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 0; w < kWarpsPerBlock - 1; ++w)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int v = 0; v < 8; ++v) r.acc[k][v] += red[w][(k * 32 + lane) * 8 + v];
+      r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed);
+    }
+    __syncthreads();
+  }
+  int64_t idx = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; idx < N; idx += step) {
+    const int64_t row = order ? order[idx] : idx;
+    r.clear();
+    r.gather(nbr, what, h, D, lane, rowptr[row], rowptr[row + 1], 0, 1);
+    r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed);
+  }
+}
+
 __global__ void act_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, int64_t n,
                                float scale, float* __restrict__ gin) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,6 +532,124 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   }
 }
 
+// SDDMM over an fp16 h table (same role as edge_grad_sddmm_kernel; D % 8 == 0, D <= 256 * K)
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+edge_grad_sddmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                           const int32_t* __restrict__ nbr, const float* __restrict__ what,
+                           const float* __restrict__ G, const __half* __restrict__ h,
+                           const float* __restrict__ tscale, const float* __restrict__ dis,
+                           const float* __restrict__ loopw, int64_t N, int D, float* __restrict__ tmp_g,
+                           float* __restrict__ tmp_t, float* __restrict__ tmp_a, const int32_t* __restrict__ order) {
+  __shared__ float red[kWarpsPerBlock];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_heavy = order ? order[N] : 0;
+  const float inv_scale = tscale[1];
+  float g_row[K][8];
+
+  auto load_row = [&](int64_t row) {
+    const float* gr = G + row * D;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        const float4 a = *reinterpret_cast<const float4*>(gr + c);
+        const float4 b = *reinterpret_cast<const float4*>(gr + c + 4);
+        g_row[k][0] = a.x * inv_scale; g_row[k][1] = a.y * inv_scale; g_row[k][2] = a.z * inv_scale;
+        g_row[k][3] = a.w * inv_scale; g_row[k][4] = b.x * inv_scale; g_row[k][5] = b.y * inv_scale;
+        g_row[k][6] = b.z * inv_scale; g_row[k][7] = b.w * inv_scale;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) g_row[k][t] = 0.f;
+      }
+    }
+  };
+  auto partial_dot = [&](const __half* hp) {
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        float x[8];
+        h8_to_float(*reinterpret_cast<const uint4*>(hp + c), x);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d = fmaf(g_row[k][t], x[t], d);
+      }
+    }
+    return d;
+  };
+  auto dot_with = [&](const __half* hp) { return warp_sum(partial_dot(hp)); };
+  auto edges = [&](int beg, int end) {
+    float tsum = 0.f;
+    int i = beg;
+    for (; i + 4 <= end; i += 4) {
+      float d0 = partial_dot(h + (int64_t)nbr[i] * D);
+      float d1 = partial_dot(h + (int64_t)nbr[i + 1] * D);
+      float d2 = partial_dot(h + (int64_t)nbr[i + 2] * D);
+      float d3 = partial_dot(h + (int64_t)nbr[i + 3] * D);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+      }
+      if (lane < 4) {
+        const float g = lane == 0 ? d0 : (lane == 1 ? d1 : (lane == 2 ? d2 : d3));
+        const int e = perm[i + lane];
+        const float t = g * what[i + lane];
+        tmp_g[e] = g;
+        tmp_t[e] = t;
+        tsum += t;
+      }
+    }
+    for (; i < end; ++i) {
+      const float g = dot_with(h + (int64_t)nbr[i] * D);
+      if (lane == 0) {
+        const int e = perm[i];
+        const float t = g * what[i];
+        tmp_g[e] = g;
+        tmp_t[e] = t;
+        tsum += t;
+      }
+    }
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+    return __shfl_sync(0xffffffffu, tsum, 0);
+  };
+  auto finish = [&](int64_t row, float tsum) {
+    const float gl = dot_with(h + row * D);
+    if (lane == 0) {
+      const float d = dis[row];
+      const float tl = gl * d * d * loopw[row];
+      tmp_a[row] = tsum + 2.0f * tl;
+    }
+  };
+  for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
+    const int64_t row = order[hidx];
+    load_row(row);
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    const int per = (((end - beg) + kWarpsPerBlock - 1) / kWarpsPerBlock + 3) & ~3;
+    const int b = min(end, beg + warp * per), e = min(end, b + per);
+    const float part = edges(b, e);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+      float tsum = 0.f;
+      for (int w = 0; w < kWarpsPerBlock; ++w) tsum += red[w];
+      finish(row, tsum);
+    }
+    __syncthreads();
+  }
+  int64_t idx = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (; idx < N; idx += step) {
+    const int64_t row = order ? order[idx] : idx;
+    load_row(row);
+    finish(row, edges(rowptr[row], rowptr[row + 1]));
+  }
+}
+
 // Phase B: add the source-side sums  A[r] += sum_{e: src_e = r} t_e
 __global__ void __launch_bounds__(kBlock)
 edge_grad_srcsum_kernel(const int32_t* __restrict__ rowptr_src, const int32_t* __restrict__ perm_src,
@@ -451,6 +748,49 @@ int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, c
   return SGS_OK;
 }
 
+int32_t sgs_table_f16(const float* in, int64_t N, int64_t D, int32_t scaled, void* out16, float* tscale,
+                      sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && D > 0 && (N * D) % 8 == 0, "N * D must be a positive multiple of 8");
+  SGS_CHECK_ARG(in && out16 && tscale, "null pointer");
+  SGS_CHECK_ARG((((uintptr_t)in | (uintptr_t)out16) & 15) == 0, "in / out16 must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int64_t n8 = N * D / 8;
+  int64_t g = ceil_div(n8, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (scaled) {
+    // tscale[2] is scratch for the absmax
+    SGS_CUDA(cudaMemsetAsync(tscale + 2, 0, sizeof(float), st));
+    table_absmax_kernel<<<(unsigned)g, 256, 0, st>>>(in, N * D / 4, tscale + 2);
+    SGS_LAUNCH_CHECK();
+  }
+  table_scale_kernel<<<1, 1, 0, st>>>(scaled ? tscale + 2 : nullptr, tscale);
+  SGS_LAUNCH_CHECK();
+  table_convert_kernel<<<(unsigned)g, 256, 0, st>>>(in, n8, tscale, reinterpret_cast<uint4*>(out16));
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_spmm_h16(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                     const float* dis, const float* loopw, const void* h16, const float* tscale, int64_t N, int64_t D,
+                     const float* bias, float* out, int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && D > 0 && D % 8 == 0 && D <= 512, "the fp16-table SpMM needs D % 8 == 0 and D <= 512");
+  SGS_CHECK_ARG(rowptr && h16 && tscale && out, "null pointer");
+  SGS_CHECK_ARG((((uintptr_t)h16 | (uintptr_t)out) & 15) == 0, "h16 / out must be 16-byte aligned");
+  SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
+  if ((flags & SGS_SPMM_DROPOUT) && p_drop == 0.f) flags &= ~SGS_SPMM_DROPOUT;
+  cudaStream_t st = as_stream(stream);
+  const __half* hh = reinterpret_cast<const __half*>(h16);
+  if (D <= 256)
+    spmm_h16_kernel<1><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias, out,
+                                                       flags, p_drop, seed, order);
+  else
+    spmm_h16_kernel<2><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias, out,
+                                                       flags, p_drop, seed, order);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
 int32_t sgs_act_bwd(const float* gout, const float* out, int64_t n, float scale, float* gin,
                     sgs_stream_t stream) {
   SGS_CHECK_ARG(n >= 0, "negative size");
@@ -482,8 +822,27 @@ static int32_t edge_grad_impl(int phases, const int32_t* rowptr_dst, const int32
                               const int32_t* perm_src, const int32_t* src, const int32_t* dst, const float* G,
                               const float* h, const float* dis, const float* deg, const float* loopw, int64_t M,
                               int64_t N, int64_t D, float* tmp_g, float* tmp_t, float* tmp_a, float* dw,
-                              int32_t accumulate, cudaStream_t st) {
-  if (phases & 1) {
+                              int32_t accumulate, cudaStream_t st, const void* h16 = nullptr,
+                              const float* tscale = nullptr) {
+  if ((phases & 1) && h16) {
+    // fp16 gather table of h (the forward's): half the gathered bytes, table L2-resident
+    if (D % 8 != 0 || D > 512) {
+      set_error("sgs_gcn_edge_grad: the fp16-table form needs D %% 8 == 0 and D <= 512");
+      return SGS_E_UNSUPPORTED;
+    }
+    const __half* hh = reinterpret_cast<const __half*>(h16);
+    if (D <= 256)
+      edge_grad_sddmm_h16_kernel<1><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, G, hh,
+                                                                    tscale, dis, loopw, N, (int)D, tmp_g, tmp_t, tmp_a,
+                                                                    order_dst);
+    else
+      edge_grad_sddmm_h16_kernel<2><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, G, hh,
+                                                                    tscale, dis, loopw, N, (int)D, tmp_g, tmp_t, tmp_a,
+                                                                    order_dst);
+    SGS_LAUNCH_CHECK();
+    edge_grad_srcsum_kernel<<<row_grid(N), kBlock, 0, st>>>(rowptr_src, perm_src, tmp_t, N, tmp_a);
+    SGS_LAUNCH_CHECK();
+  } else if (phases & 1) {
     const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)G) % 16 == 0);
 #define SGS_SDDMM_LAUNCH(VEC, K)                                                                         \
   edge_grad_sddmm_kernel<VEC, K><<<row_grid(N), kBlock, 0, st>>>(rowptr_dst, perm_dst, nbr_dst, what_dst, \
@@ -530,6 +889,23 @@ int32_t sgs_gcn_edge_grad(const int32_t* rowptr_dst, const int32_t* perm_dst, co
                 "null pointer");
   return edge_grad_impl(3, rowptr_dst, perm_dst, nbr_dst, what_dst, order_dst, rowptr_src, perm_src, src, dst, G, h,
                         dis, deg, loopw, M, N, D, tmp_g, tmp_t, tmp_a, dw, accumulate, as_stream(stream));
+}
+
+int32_t sgs_gcn_edge_grad_h16(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
+                              const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
+                              const int32_t* perm_src, const int32_t* src, const int32_t* dst, const float* G,
+                              const void* h16, const float* tscale, const float* dis, const float* deg,
+                              const float* loopw, int64_t M, int64_t N, int64_t D, float* tmp_g, float* tmp_t,
+                              float* tmp_a, float* dw, int32_t accumulate, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && M >= 0 && D > 0, "bad sizes");
+  if (M == 0) return SGS_OK;
+  SGS_CHECK_ARG(rowptr_dst && perm_dst && nbr_dst && what_dst && rowptr_src && perm_src && src && dst && G && h16 &&
+                    tscale && dis && deg && loopw && tmp_g && tmp_t && tmp_a && dw,
+                "null pointer");
+  SGS_CHECK_ARG((((uintptr_t)h16 | (uintptr_t)G) & 15) == 0, "G / h16 must be 16-byte aligned");
+  return edge_grad_impl(3, rowptr_dst, perm_dst, nbr_dst, what_dst, order_dst, rowptr_src, perm_src, src, dst, G,
+                        nullptr, dis, deg, loopw, M, N, D, tmp_g, tmp_t, tmp_a, dw, accumulate, as_stream(stream), h16,
+                        tscale);
 }
 
 int32_t sgs_gcn_edge_grad_partial(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,

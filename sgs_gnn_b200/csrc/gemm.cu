@@ -83,9 +83,47 @@ __global__ void zero_rows_kernel(float* __restrict__ C, int64_t ldc, int M, int 
   for (; i < total; i += stride) C[(i / N) * ldc + (i % N)] = 0.f;
 }
 
+// tcgen05 kind::tf32 reads the upper 19 bits of each fp32 operand, i.e. it TRUNCATES the mantissa: a biased error of
+// up to 2^-10 per product that does not average out over K.  Rounding the operands to the nearest tf32 value first
+// (cvt.rna) makes the error unbiased, so it shrinks with sqrt(K) -- what keeps the tensor-core path inside the fp32
+// 1e-4 parity bar (measured r02: 1.8e-4 -> see tests/test_gpu_tc.py).
+__global__ void round_tf32_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  if ((((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    for (int64_t k = i; k < n4; k += stride) {
+      float4 v = reinterpret_cast<const float4*>(in)[k];
+      uint32_t a, b, c, d;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w));
+      reinterpret_cast<uint4*>(out)[k] = make_uint4(a, b, c, d);
+    }
+    i += n4 * 4;
+  }
+  for (; i < n; i += stride) {
+    uint32_t a;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(in[i]));
+    out[i] = __uint_as_float(a);
+  }
+}
+
 }  // namespace sgs
 
 using namespace sgs;
+
+extern "C" int32_t sgs_round_tf32(const float* in, int64_t n, float* out, sgs_stream_t stream) {
+  SGS_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return SGS_OK;
+  SGS_CHECK_ARG(in && out, "null pointer");
+  int64_t g = ceil_div(n / 4 + 1, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  round_tf32_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, as_stream(stream)>>>(in, n, out);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
 
 extern "C" int32_t sgs_gemm(const float* A, int64_t a_sm, int64_t a_sk, const float* B, int64_t b_sn,
                             int64_t b_sk, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,

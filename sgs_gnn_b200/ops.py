@@ -20,16 +20,23 @@ from ._lib import (PREC_BF16, PREC_FP16, PREC_FP32, PREC_TF32, SAMPLE_RAW, SAMPL
 # configuration
 # ------------------------------------------------------------------------------------------
 _PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "tf32": PREC_TF32}
-_state = {"gemm": PREC_FP32, "scorer": PREC_FP32}
+_state = {"gemm": PREC_FP32, "scorer": PREC_FP32, "gather": PREC_FP32}
 
 
-def set_precision(gemm=None, scorer=None):
+def set_precision(gemm=None, scorer=None, gather=None):
     """Precision of the dense contractions: 'fp32' (CUDA cores, parity mode) or a tcgen05
-    tensor-core mode ('bf16' / 'fp16' / 'tf32')."""
+    tensor-core mode ('bf16' / 'fp16' / 'tf32').
+    gather: storage of the rows the wide (D >= 64) SpMM / SDDMM gather -- 'fp32' (the [N,D] tensor as it is) or
+    'fp16' (a 16-bit copy with a power-of-two scale that stays L2-resident; fp32 accumulation)."""
     if gemm is not None:
         _state["gemm"] = _PRECISION[gemm] if isinstance(gemm, str) else int(gemm)
     if scorer is not None:
         _state["scorer"] = _PRECISION[scorer] if isinstance(scorer, str) else int(scorer)
+    if gather is not None:
+        g = _PRECISION[gather] if isinstance(gather, str) else int(gather)
+        if g not in (PREC_FP32, PREC_FP16):
+            raise ValueError("gather precision must be 'fp32' or 'fp16'")
+        _state["gather"] = g
 
 
 def scorer_supports(precision):
@@ -383,26 +390,42 @@ def gemm(a, a_sm, a_sk, b, b_sn, b_sk, m, n, k, out=None, accumulate=False, prec
 _pad_cache = {}
 
 
-def _rows_aligned16(t, cache=False):
-    """TMA needs 16-byte aligned row strides: returns (tensor, ld) with ld % 4 == 0, copying into a padded
-    buffer when the row length is odd (e.g. F = 602).  Static inputs (node features) are padded once."""
+def round_tf32(t, out=None):
+    """t rounded to the nearest tf32 value (sgs_round_tf32): unbiased operands for the truncating kind::tf32 MMA."""
+    t = _req(t, torch.float32, "tensor")
+    if out is None:
+        out = torch.empty_like(t)
+    check(lib().sgs_round_tf32(_p(t), t.numel(), _p(out), _stream()), "sgs_round_tf32")
+    return out
+
+
+def _tf32_operand(t, static=False):
+    """Operand of a kind::tf32 GEMM: (tensor, ld) with a 16-byte aligned row stride (TMA; odd row lengths such as
+    F = 602 are padded) and values rounded to the nearest tf32.  Static inputs (node features) are prepared once."""
     k = t.size(1)
-    if k % 4 == 0 and t.data_ptr() % 16 == 0:
-        return t, k
-    if cache:
+    if static:
         key = id(t)
         hit = _pad_cache.get(key)
         if hit is not None and hit[0]() is t and hit[1] == t._version:
             return hit[2], hit[2].size(1)
-    ld = (k + 3) // 4 * 4
-    buf = torch.zeros(t.size(0), ld, dtype=t.dtype, device=t.device)
-    buf[:, :k].copy_(t)
-    if cache:
+    if k % 4 == 0 and t.data_ptr() % 16 == 0 and t.is_contiguous():
+        buf = round_tf32(t)
+    else:
+        ld = (k + 3) // 4 * 4
+        buf = torch.zeros(t.size(0), ld, dtype=t.dtype, device=t.device)
+        buf[:, :k].copy_(t)
+        round_tf32(buf, out=buf)
+    if static:
         try:
             _pad_cache[key] = (weakref.ref(t, lambda _r, kk=key, c=_pad_cache: c.pop(kk, None)), t._version, buf)
         except TypeError:
             pass
-    return buf, ld
+    return buf, buf.size(1)
+
+
+def _rows_aligned16(t, cache=False):
+    """(tensor, ld) with ld % 4 == 0 for TMA, tf32-rounded (see _tf32_operand)."""
+    return _tf32_operand(t, static=cache)
 
 
 def linear_nt(x, w, precision=None, static_x=False):
@@ -412,8 +435,8 @@ def linear_nt(x, w, precision=None, static_x=False):
     prec = _state["gemm"] if precision is None else precision
     m, k, n = x.size(0), x.size(1), w.size(0)
     if prec == PREC_TF32:
-        xa, lda = _rows_aligned16(x, cache=static_x)
-        wa, ldb = _rows_aligned16(w)
+        xa, lda = _tf32_operand(x, static=static_x)
+        wa, ldb = _tf32_operand(w)
         return gemm(xa, lda, 1, wa, ldb, 1, m, n, k, precision=prec)
     return gemm(x, k, 1, w, k, 1, m, n, k, precision=prec)
 
@@ -423,8 +446,8 @@ def linear_nt_into(x, w, out, precision=None):
     prec = _state["gemm"] if precision is None else precision
     m, k, n = x.size(0), x.size(1), w.size(0)
     if prec != PREC_FP32:
-        xa, lda = _rows_aligned16(x)
-        wa, ldb = _rows_aligned16(w)
+        xa, lda = _tf32_operand(x)
+        wa, ldb = _tf32_operand(w)
         return gemm(xa, lda, 1, wa, ldb, 1, m, n, k, out=out, precision=PREC_TF32)
     return gemm(x, k, 1, w, k, 1, m, n, k, out=out, precision=prec)
 
@@ -433,25 +456,60 @@ def gemm_tn(a, b, out=None, static_b=False, precision=None):
     """out[M,N] = a[K,M]^T @ b[K,N] (weight gradients dW = dh^T x: a reduction over the K node rows).
     Tensor-core mode: tcgen05 kind::tf32 with MN-major operands straight from the row-major tensors, K split
     over the CTAs; needs 16-byte aligned row strides (odd widths fall back to the fp32 split-K kernel, a static
-    `b` such as the node features is padded once)."""
+    `b` such as the node features is padded once).  Operands are rounded to the nearest tf32 first."""
     prec = _state["gemm"] if precision is None else precision
     k, m = a.shape
     n = b.size(1)
     if prec != PREC_FP32 and m % 4 == 0 and a.data_ptr() % 16 == 0:
-        bb, ldb = (b, n) if (n % 4 == 0 and b.data_ptr() % 16 == 0) else (_rows_aligned16(b, cache=True) if static_b
-                                                                          else (None, 0))
-        if bb is not None:
-            return gemm(a, 1, m, bb, 1, ldb, m, n, k, out=out, precision=PREC_TF32)
+        if n % 4 == 0 and b.data_ptr() % 16 == 0 or static_b:
+            bb, ldb = _tf32_operand(b, static=static_b)
+            aa = round_tf32(a if a.is_contiguous() else a.contiguous())
+            return gemm(aa, 1, m, bb, 1, ldb, m, n, k, out=out, precision=PREC_TF32)
     return gemm(a, 1, m, b, 1, n, m, n, k, out=out, precision=PREC_FP32)
 
 
-def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False, add_root=False):
+class GatherTable:
+    """fp16 copy of an [N, D] fp32 tensor whose rows a SpMM / SDDMM gathers (sgs_table_f16): `data` int16-typed
+    storage [N, D], `scale` device float[4] = {S, 1/S, scratch, -}."""
+    __slots__ = ("data", "scale")
+
+    def __init__(self, data, scale):
+        self.data, self.scale = data, scale
+
+
+def gather_table(h, scaled=False):
+    """The fp16 gather table of `h` when the gather precision is 'fp16' and the width qualifies (D % 8 == 0,
+    64 <= D <= 512: narrower tables are L2-resident in fp32 already), else None.  scaled: gradient tables get a
+    power-of-two scale from max|h| (fp16 range), activations are stored as they are."""
+    if _state["gather"] != PREC_FP16:
+        return None
+    n, d = h.shape
+    if d % 8 or d < 64 or d > 512 or (n * d) % 8:
+        return None
+    h = _req(h, torch.float32, "h")
+    data = torch.empty(n, d, dtype=torch.int16, device=h.device)
+    scale = torch.empty(4, dtype=torch.float32, device=h.device)
+    with _timed("table_f16"):
+        check(lib().sgs_table_f16(_p(h), n, d, 1 if scaled else 0, _p(data), _p(scale), _stream()), "sgs_table_f16")
+    return GatherTable(data, scale)
+
+
+def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False, add_root=False,
+         table=None):
+    """K3b.  `table`: the GatherTable of `h` (fp16 gather mode) -- the neighbour rows and the self term then come
+    from it instead of from `h`."""
     rowptr, _perm, nbr, order = csr
     n, d = h.shape
     if out is None:
         out = torch.empty(n, d, dtype=torch.float32, device=h.device)
     flags = ((SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0) |
              (SPMM_ADD_ROOT if add_root else 0))
+    if table is not None:
+        with _timed(f"spmm_d{d}"):
+            check(lib().sgs_spmm_h16(_p(rowptr), _p(nbr), _p(what), _p(order), _p(norm.dis) if norm is not None else None,
+                                     _p(norm.loopw) if norm is not None else None, _p(table.data), _p(table.scale), n,
+                                     d, _p(bias), _p(out), flags, float(p_drop), int(seed), _stream()), "sgs_spmm_h16")
+        return out
     with _timed(f"spmm_d{d}"):
         check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(order), _p(norm.dis) if norm is not None else None,
                              _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
@@ -473,10 +531,12 @@ class GCNConvFn(torch.autograd.Function):
             raise RuntimeError("x must have one row per node")
         norm = graph.norm(edge_weight)
         h = linear_nt(x, weight, static_x=not x.requires_grad)
-        out = spmm(graph.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed)
+        tab = gather_table(h)
+        out = spmm(graph.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed, table=tab)
         ctx.graph, ctx.norm, ctx.relu, ctx.p_drop = graph, norm, relu, p_drop
         ctx.has_w = edge_weight is not None
-        ctx.save_for_backward(x, weight, h if ctx.has_w else None, out if relu else None)
+        ctx.tab = tab if ctx.has_w else None      # the edge-weight gradient gathers the same rows again
+        ctx.save_for_backward(x, weight, h if (ctx.has_w and tab is None) else None, out if relu else None)
         return out
 
     @staticmethod
@@ -497,7 +557,7 @@ class GCNConvFn(torch.autograd.Function):
             db = torch.empty(d, dtype=torch.float32, device=g.device)
             check(lib().sgs_colsum(_p(g), n, d, _p(db), _stream()), "sgs_colsum")
         if need_w or need_x:
-            dh = spmm(graph.csr_src, norm.what_src, norm, g)
+            dh = spmm(graph.csr_src, norm.what_src, norm, g, table=gather_table(g, scaled=True))
             fin = x.size(1)
             if need_w:  # dW[d, fin] = dh^T x
                 dw = gemm_tn(dh, x, static_b=not x.requires_grad)
@@ -514,11 +574,19 @@ class GCNConvFn(torch.autograd.Function):
             rp_d, pm_d, nb_d, od_d = graph.csr_dst
             rp_s, pm_s, _, _ = graph.csr_src
             with _timed(f"edge_grad_d{d}"):
-                check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(od_d), _p(rp_s),
-                                              _p(pm_s),
-                                              _p(graph.src), _p(graph.dst), _p(g), _p(h), _p(norm.dis),
-                                              _p(norm.deg), _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]),
-                                              _p(tmp[2 * m:]), _p(dew), 0, _stream()), "sgs_gcn_edge_grad")
+                if ctx.tab is not None:
+                    check(lib().sgs_gcn_edge_grad_h16(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(od_d),
+                                                      _p(rp_s), _p(pm_s), _p(graph.src), _p(graph.dst), _p(g),
+                                                      _p(ctx.tab.data), _p(ctx.tab.scale), _p(norm.dis), _p(norm.deg),
+                                                      _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]), _p(tmp[2 * m:]),
+                                                      _p(dew), 0, _stream()), "sgs_gcn_edge_grad_h16")
+                else:
+                    check(lib().sgs_gcn_edge_grad(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(od_d), _p(rp_s),
+                                                  _p(pm_s),
+                                                  _p(graph.src), _p(graph.dst), _p(g), _p(h), _p(norm.dis),
+                                                  _p(norm.deg), _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]),
+                                                  _p(tmp[2 * m:]), _p(dew), 0, _stream()), "sgs_gcn_edge_grad")
+            ctx.tab = None
         return dx, dw, db, dew, None, None, None, None
 
 
@@ -603,29 +671,35 @@ def sage_conv(x, w_l, b_l, w_r, graph, relu=False, p_drop=0.0, seed=0):
 # edge scorer
 # ------------------------------------------------------------------------------------------
 
-def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0, precision=None):
-    """p[n] for edges `ids` (int32) or all edges of `graph` (no autograd)."""
+def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0, precision=None, want_gates=False):
+    """p[n] for edges `ids` (int32) or all edges of `graph` (no autograd).
+    want_gates: also return the GATE BITS of these edges (uint8 [n, H/8]; sgs_edge_score_fwd_gates) -- what a later
+    backward over a subset of them needs instead of a recompute -- or None when the mode cannot produce them."""
     prec = _state["scorer"] if precision is None else precision
     out = _req(out, torch.float32, "out")
     n_nodes, h = out.shape
     n = graph.num_edges if ids is None else int(ids.numel())
     p = _vec(n, torch.float32, out.device)
+    gates = None
+    if want_gates and n > 0 and lib().sgs_edge_score_gate_bytes(n, h, prec) > 0:
+        gates = torch.empty(n, h // 8, dtype=torch.uint8, device=out.device)
     nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, prec, 0)
     ws = _ws(nbytes, out.device, "edge_score_fwd")
     with _timed("edge_score_fwd"):
-        check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
-                                       _p(b1), _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(ws), ws.numel(),
-                                       prec, _stream()), "sgs_edge_score_fwd")
-    return p
+        check(lib().sgs_edge_score_fwd_gates(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
+                                             _p(b1), _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(gates),
+                                             _p(ws), ws.numel(), prec, _stream()), "sgs_edge_score_fwd")
+    return (p, gates) if want_gates else p
 
 
 class EdgeScoreFn(torch.autograd.Function):
     """_edge_score (model.py:115-122) over all edges or an id subset.  `precomputed` lets the
     hybrid pipeline reuse the no-grad full-graph probabilities for the forward value while the
-    backward still runs (recompute + gradient) over just these edges."""
+    backward still runs (gradient) over just these edges; `gates` are the gate bits that forward left over ALL edges
+    of `graph` (the backward then needs no recompute of the hidden layer)."""
 
     @staticmethod
-    def forward(ctx, out, w1, b1, w2, b2, graph, ids, p_drop, seed, precomputed, precision):
+    def forward(ctx, out, w1, b1, w2, b2, graph, ids, p_drop, seed, precomputed, precision, gates):
         ctx.w2_shape, ctx.b2_shape = w2.shape, b2.shape
         w1 = _req(w1, torch.float32, "fc1.weight")
         b1 = _req(b1, torch.float32, "fc1.bias")
@@ -633,11 +707,14 @@ class EdgeScoreFn(torch.autograd.Function):
         b2 = _req(b2.reshape(-1), torch.float32, "fc2.bias")
         out = _req(out, torch.float32, "out")
         if precomputed is None:
-            p = edge_score_forward(out, graph, w1, b1, w2, b2, ids, p_drop, seed, precision)
+            # gate bits of exactly these edges: rows are indexed by position, so they only fit an ids-free backward
+            p, gates = edge_score_forward(out, graph, w1, b1, w2, b2, ids, p_drop, seed, precision,
+                                          want_gates=ids is None and any(ctx.needs_input_grad[:5]))
         else:
             p = precomputed
         ctx.graph, ctx.ids, ctx.p_drop, ctx.seed = graph, ids, p_drop, seed
         ctx.prec = _state["scorer"] if precision is None else precision
+        ctx.gates = gates
         ctx.save_for_backward(out, w1, b1, w2, b2, p)
         return p
 
@@ -654,18 +731,24 @@ class EdgeScoreFn(torch.autograd.Function):
         small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
         nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, ctx.prec, 1)
         ws = _ws(nbytes, dev, "edge_score_bwd")
+        gates = ctx.gates
+        if gates is not None and lib().sgs_edge_score_gate_bytes(n, h, ctx.prec) == 0:
+            gates = None
         with _timed("edge_score_bwd"):
-            check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
-                                           _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(p_fwd),
-                                           _p(dp), _p(d_out), _p(dw1), _p(small), _p(small[h:]),
-                                           _p(small[2 * h:]), _p(ws), ws.numel(), ctx.prec, _stream()),
-                      "sgs_edge_score_bwd")
+            check(lib().sgs_edge_score_bwd_gates(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
+                                                 _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(p_fwd),
+                                                 _p(dp), _p(gates), _p(d_out), _p(dw1), _p(small), _p(small[h:]),
+                                                 _p(small[2 * h:]), _p(ws), ws.numel(), ctx.prec, _stream()),
+                  "sgs_edge_score_bwd")
+        ctx.gates = None
         db1, dw2, db2 = small[:h], small[h:2 * h].reshape(ctx.w2_shape), small[2 * h:].reshape(ctx.b2_shape)
-        return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None
+        return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None, None
 
 
-def edge_score(out, w1, b1, w2, b2, graph, ids=None, p_drop=0.0, seed=0, precomputed=None, precision=None):
-    return EdgeScoreFn.apply(out, w1, b1, w2, b2, graph, ids, float(p_drop), int(seed), precomputed, precision)
+def edge_score(out, w1, b1, w2, b2, graph, ids=None, p_drop=0.0, seed=0, precomputed=None, precision=None,
+               gates=None):
+    return EdgeScoreFn.apply(out, w1, b1, w2, b2, graph, ids, float(p_drop), int(seed), precomputed, precision,
+                             gates)
 
 
 # ------------------------------------------------------------------------------------------

@@ -315,7 +315,7 @@ class ShardedGCNConvFn(torch.autograd.Function):
             if hi > lo:
                 ops.linear_nt_into(x[lo:hi], weight, h[lo:hi])
             lg.comm.exchange_rows(h, lg.bounds)
-        out = ops.spmm(g.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed)
+        out = ops.spmm(g.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed, table=ops.gather_table(h))
         if exchange_out:
             lg.comm.exchange_rows(out, lg.bounds)
         ctx.lg, ctx.norm, ctx.relu, ctx.p_drop, ctx.exchange_out = lg, norm, relu, p_drop, exchange_out
@@ -349,7 +349,8 @@ class ShardedGCNConvFn(torch.autograd.Function):
             if ns > 0:
                 check(lib().sgs_colsum(_p(g_full[lo:hi]), ns, d, _p(db), _stream()), "sgs_colsum")
         if need_w or need_x:
-            dh = ops.spmm(g.csr_src, norm.what_src, norm, g_full)       # partial sums for arbitrary rows
+            dh = ops.spmm(g.csr_src, norm.what_src, norm, g_full,      # partial sums for arbitrary rows
+                          table=ops.gather_table(g_full, scaled=True))
             dh_slab = comm.reduce_rows(dh, bounds)
             if need_w:
                 dw = torch.zeros_like(weight)
@@ -486,17 +487,17 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
     p_drop = scorer._drop()
     fc1, fc2 = scorer.fc1, scorer.fc2
     with torch.no_grad():
-        p_loc = ops.edge_score_forward(out.detach(), g_loc, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
-                                       fc2.bias.reshape(-1), None, p_drop, seed_sc)
+        p_loc, gates = ops.edge_score_forward(out.detach(), g_loc, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
+                                              fc2.bias.reshape(-1), None, p_drop, seed_sc, want_gates=True)
 
     smp = topq.select_ex(p_loc, sb.prob, draw_noise(), q, SAMPLE_TRAIN, coef, S=sampling._next_S(), gid=sb.gid)
     _check(smp.invalid, smp.n_global, q)
     lg_s = lg.subgraph(smp.sel)
     if pipeline == "hybrid":
         p_sel = ops.gather_selected(p_loc, None, smp.sel, SAMPLE_RAW, 0.0, None)[0]
-        p_s = scorer.score(out, g_loc, ids=smp.sel, precomputed=p_sel, seed=seed_sc)
+        p_s = scorer.score(out, g_loc, ids=smp.sel, precomputed=p_sel, seed=seed_sc, gates=gates)
     elif pipeline == "straight_through":
-        p_full_g = scorer.score(out, g_loc, precomputed=p_loc, seed=seed_sc)
+        p_full_g = scorer.score(out, g_loc, precomputed=p_loc, seed=seed_sc, gates=gates)
         p_s = ShardedStraightThroughFn.apply(p_full_g, sb.prob, smp.sel, smp.S, SAMPLE_TRAIN, coef, comm)
     else:
         raise ValueError(pipeline)

@@ -3,12 +3,15 @@ against the REFERENCE's own fp32 training loop (golden trajectories step_hybrid_
 by tests/golden/make_golden.py from the unmodified reference at H = 256 with the Exp(1) noise tensors recorded).
 
 Stated bounds for reduced-precision operands (north_star: "stated looser bound for bf16 GEMM inputs"); every measured
-figure is also written to gpurun_out/parity_benched.json so the bounds can be audited:
+figure is also written to gpurun_out/parity_benched.json (committed copy: profiles/r02_parity_benched.json):
   * the conditional-gate branch decision of every epoch equals the reference's,
   * per-epoch loss within LOSS_RTOL of the reference's,
-  * edge probabilities handed to the sampler within P_ATOL (abs) of the reference's, every epoch,
+  * edge probabilities handed to the sampler: first epoch (identical weights) within P0_ATOL (abs) of the
+    reference's; later epochs within P_ATOL (the weights themselves have drifted by then, see PARAM_TOL),
   * sampled-set overlap with the reference's mask >= OVERLAP_MIN, every epoch (same injected noise),
-  * final parameters after 6 Adam epochs within PARAM_TOL * (1 + max|ref|).
+  * final parameters after 6 Adam epochs within PARAM_TOL * (1 + max|ref|).  Adam normalises every element's step
+    to ~lr, so an element whose gradient is rounding noise can move by lr per epoch in either direction whatever the
+    precision: the bound is 2 * lr * epochs = 1.2e-2 (measured 0.8e-2 .. 1.1e-2 in every mode, tf32 included).
 """
 import json
 import os
@@ -23,11 +26,11 @@ from conftest import ROOT, FixtureBatch, load_golden, t
 
 pytestmark = pytest.mark.gpu
 
-# measured on B200 (gpurun_out/parity_benched.json, round 2) with ~3x head-room
+# measured on B200 (round 2; loss <= 3.5e-4 / 1.3e-3 bf16, p0 6e-5 / 2e-4 bf16, overlap >= 0.99925) with head-room
 BOUNDS = {
-    "fp16": dict(LOSS_RTOL=5e-3, P_ATOL=1e-3, OVERLAP_MIN=0.995, PARAM_TOL=2e-3),
-    "bf16": dict(LOSS_RTOL=2e-2, P_ATOL=8e-3, OVERLAP_MIN=0.97, PARAM_TOL=4e-3),
-    "tf32": dict(LOSS_RTOL=1e-3, P_ATOL=1e-4, OVERLAP_MIN=0.999, PARAM_TOL=1e-3),
+    "fp16": dict(LOSS_RTOL=1e-3, P0_ATOL=2e-4, P_ATOL=1e-2, OVERLAP_MIN=0.999, PARAM_TOL=1.2e-2),
+    "bf16": dict(LOSS_RTOL=4e-3, P0_ATOL=6e-4, P_ATOL=2e-2, OVERLAP_MIN=0.998, PARAM_TOL=1.2e-2),
+    "tf32": dict(LOSS_RTOL=1e-3, P0_ATOL=1e-4, P_ATOL=1e-2, OVERLAP_MIN=0.999, PARAM_TOL=1.2e-2),
 }
 
 
@@ -58,9 +61,10 @@ def _record(tag, rec):
         pass
 
 
+@pytest.mark.parametrize("gather", ["fp16", "fp32"])
 @pytest.mark.parametrize("scorer", ["fp16", "bf16", "tf32"])
 @pytest.mark.parametrize("name,pipeline", [("step_hybrid_h256.npz", "hybrid"), ("step_st_h256.npz", "straight_through")])
-def test_benched_precision_trajectory_vs_reference(dev, name, pipeline, scorer, monkeypatch):
+def test_benched_precision_trajectory_vs_reference(dev, name, pipeline, scorer, gather, monkeypatch):
     from sgs_gnn_b200 import _train_core, ops, sampling, training
     from sgs_gnn_b200.model import GNNModel
     if scorer == "tf32" and not ops.scorer_supports("tf32"):
@@ -71,7 +75,7 @@ def test_benched_precision_trajectory_vs_reference(dev, name, pipeline, scorer, 
     f, c, h, q = b.x.size(1), int(b.y.max()) + 1, int(z["hidden"]), int(z["q"])
     e = b.edge_index.size(1)
     assert h == 256
-    ops.set_precision(gemm="tf32", scorer=scorer)
+    ops.set_precision(gemm="tf32", scorer=scorer, gather=gather)
     model = GNNModel(f, h, c, 0.0, "GCN")
     model.load_state_dict({k[4:]: t(v) for k, v in z.items() if k.startswith("sd0.")})
     model = model.to(dev)
@@ -114,9 +118,10 @@ def test_benched_precision_trajectory_vs_reference(dev, name, pipeline, scorer, 
             perr[k[4:]] = float((got - want).abs().max()) / (1.0 + float(want.abs().max()))
     rec["param_err_max"] = max(perr.values())
     rec["param_err"] = perr
-    _record(f"{pipeline}/{scorer}", rec)
+    _record(f"{pipeline}/scorer={scorer}/gemm=tf32/gather={gather}", rec)
     assert all(rec["branch_equal"]), rec
     assert max(rec["loss_rel"]) < bd["LOSS_RTOL"], rec
+    assert rec["p_abs"][0] < bd["P0_ATOL"], rec
     assert max(rec["p_abs"]) < bd["P_ATOL"], rec
     assert min(rec["overlap"]) >= bd["OVERLAP_MIN"], rec
     assert rec["param_err_max"] < bd["PARAM_TOL"], rec
