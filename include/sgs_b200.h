@@ -201,22 +201,6 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
                            float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream);
 
-/* Gate bits: what the hybrid pipeline keeps from the forward over ALL edges so that the backward over the q sampled
- * ones (training_hybrid.py:86 `edge_probs_full[mask]` -> autograd) needs no recompute of the hidden layer.
- * gates[e, j / 8] bit (j % 8) = [hidden pre-activation j of edge e > 0] * [dropout keeps it]; H / 8 bytes per edge,
- * indexed by the position in the forward's edge list.  sgs_edge_score_gate_bytes returns 0 when the mode cannot
- * produce them (then pass gates = NULL and the backward recomputes).  The backward's `gates` is the forward's array
- * over the SAME (src, dst, ids = NULL) list; its own `ids` pick the rows. */
-size_t sgs_edge_score_gate_bytes(int64_t n, int64_t H, int32_t precision);
-int32_t sgs_edge_score_fwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
-                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                                 const float* b2, float p_drop, uint64_t seed, float* p, void* gates, void* ws,
-                                 size_t ws_bytes, int32_t precision, sgs_stream_t stream);
-int32_t sgs_edge_score_bwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
-                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                                 const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
-                                 const void* gates, float* d_out, float* dW1, float* db1, float* dw2, float* db2,
-                                 void* ws, size_t ws_bytes, int32_t precision, sgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 sampler  (sampling.py:91-155 gumbel_softmax_sampling + the compaction at

@@ -48,10 +48,6 @@ SIGNATURES = {
     "sgs_edge_score_fwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, SZ, I32, P]),
     "sgs_edge_score_bwd": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, P, P, P, P, P, SZ,
                                  I32, P]),
-    "sgs_edge_score_gate_bytes": (SZ, [I64, I64, I32]),
-    "sgs_edge_score_fwd_gates": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, SZ, I32, P]),
-    "sgs_edge_score_bwd_gates": (I32, [P, I64, I64, P, P, P, I64, P, P, P, P, F32, U64, P, P, P, P, P, P, P, P, P,
-                                       SZ, I32, P]),
     "sgs_sum_f32": (I32, [P, I64, P, P, SZ, P]),
     "sgs_softmax_f32": (I32, [P, I64, P, P, SZ, P]),
     "sgs_exponential_f32": (I32, [P, I64, U64, P]),

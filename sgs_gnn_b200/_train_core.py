@@ -93,11 +93,9 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     seed_sc = ops.next_seed()
     p_drop = scorer._drop()
     fc1, fc2 = scorer.fc1, scorer.fc2
-    # (hybrid / straight_through: the gate bits of this pass are all the later backward needs from it)
-    keep_gates = pipeline in ("hybrid", "straight_through") and torch.is_grad_enabled()
     with torch.no_grad():
-        p_full, gates = ops.edge_score_forward(out.detach(), g_full, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
-                                               fc2.bias.reshape(-1), None, p_drop, seed_sc, want_gates=keep_gates)
+        p_full = ops.edge_score_forward(out.detach(), g_full, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
+                                        fc2.bias.reshape(-1), None, p_drop, seed_sc)
     ops.seg_end(profiler, "edge_score")
 
     # sample (training_hybrid.py:72-83)
@@ -106,7 +104,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     if pipeline == "hybrid":
         # edge_probs_full[mask] with grad (training_hybrid.py:86): backward over the q edges only
         p_sel = ops.gather_selected(p_full, None, smp.sel, ops.SAMPLE_RAW, 0.0, None)[0]
-        p_s = scorer.score(out, g_full, ids=smp.sel, precomputed=p_sel, seed=seed_sc, gates=gates)
+        p_s = scorer.score(out, g_full, ids=smp.sel, precomputed=p_sel, seed=seed_sc)
     elif pipeline == "two_pass":
         # pass 3 (training_two_pass.py:75-81): the scorer runs again on the sampled subgraph itself -- message
         # passing over the q sampled edges, scoring of those q edges, fresh dropout masks, gradients enabled
@@ -115,7 +113,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     elif pipeline == "straight_through":
         # sampled_edge_weight = (p * st)[mask].clamp(0,1) with dense gradient
         # (training_straight_through.py:60-75, sampling.py:137-155)
-        p_full_g = scorer.score(out, g_full, precomputed=p_full, seed=seed_sc, gates=gates)
+        p_full_g = scorer.score(out, g_full, precomputed=p_full, seed=seed_sc)
         p_s = ops.StraightThroughWeightsFn.apply(p_full_g, batch.prob, smp.sel, smp.S, SAMPLE_TRAIN, coef)
     else:
         raise ValueError(pipeline)

@@ -11,16 +11,15 @@ namespace sgs {
 
 int32_t edge_score_fwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                           const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                          const float* b2, float p_drop, uint64_t seed, float* p, uint32_t* mask, void* ws,
-                          size_t ws_bytes, int32_t precision, cudaStream_t st);
-bool edge_score_gate_bits_supported(int64_t H, int32_t precision);
+                          const float* b2, float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes,
+                          int32_t precision, cudaStream_t st);
 size_t edge_score_tc_workspace_bytes(int64_t n, int64_t N, int64_t H);
 size_t edge_score_bwd_tc_workspace_bytes(int64_t n, int64_t N, int64_t H);
 int32_t edge_score_bwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                           const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
                           float p_drop, uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
-                          float* db1, float* dw2, float* db2, const uint32_t* mask, void* ws, size_t ws_bytes,
-                          int32_t precision, cudaStream_t st);
+                          float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int32_t precision,
+                          cudaStream_t st);
 static inline bool tc_bwd_supported(int32_t precision, int64_t H) {
   return (precision == SGS_PREC_BF16 || precision == SGS_PREC_FP16) && (H == 128 || H == 256);
 }
@@ -241,34 +240,18 @@ size_t sgs_edge_score_workspace_bytes(int64_t n, int64_t N, int64_t H, int32_t p
   return (size_t)chunk * per_edge_bytes(H, backward) + 256 + 2 * ((size_t)2 * H * H * sizeof(float) + 256);
 }
 
-size_t sgs_edge_score_gate_bytes(int64_t n, int64_t H, int32_t precision) {
-  if (n <= 0 || !edge_score_gate_bits_supported(H, precision)) return 0;
-  return (size_t)n * (size_t)(H / 8);
-}
-
 int32_t sgs_edge_score_fwd(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                            const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
                            const float* b2, float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream) {
-  return sgs_edge_score_fwd_gates(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, nullptr, ws, ws_bytes,
-                                  precision, stream);
-}
-
-int32_t sgs_edge_score_fwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
-                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                                 const float* b2, float p_drop, uint64_t seed, float* p, void* gates, void* ws,
-                                 size_t ws_bytes, int32_t precision, sgs_stream_t stream) {
   SGS_CHECK_ARG(n >= 0 && N > 0 && H > 0 && H % 4 == 0, "bad sizes (H must be a multiple of 4)");
   if (n == 0) return SGS_OK;
   SGS_CHECK_ARG(out && src && dst && W1 && b1 && w2 && b2 && p && ws, "null pointer");
   SGS_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "p_drop must be in [0,1)");
-  SGS_CHECK_ARG(!gates || edge_score_gate_bits_supported(H, precision),
-                "gate bits need H = 256 and a 16-bit tensor-core precision (see sgs_edge_score_gate_bytes)");
-  SGS_CHECK_ARG(((uintptr_t)gates & 15) == 0, "gates must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (is_16bit(precision))
-    return edge_score_fwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p,
-                             reinterpret_cast<uint32_t*>(gates), ws, ws_bytes, precision, st);
+    return edge_score_fwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, ws, ws_bytes,
+                             precision, st);
   SGS_CHECK_ARG(precision == SGS_PREC_FP32 || precision == SGS_PREC_TF32, "unknown precision");
   const int32_t gprec = precision == SGS_PREC_TF32 ? SGS_PREC_TF32 : SGS_PREC_FP32;
   const size_t pe = per_edge_bytes(H, 0);
@@ -314,18 +297,7 @@ int32_t sgs_edge_score_bwd(const float* out, int64_t N, int64_t H, const int32_t
                            const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
                            float* d_out, float* dW1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
                            int32_t precision, sgs_stream_t stream) {
-  return sgs_edge_score_bwd_gates(out, N, H, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p_fwd, dp, nullptr, d_out,
-                                  dW1, db1, dw2, db2, ws, ws_bytes, precision, stream);
-}
-
-int32_t sgs_edge_score_bwd_gates(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
-                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                                 const float* b2, float p_drop, uint64_t seed, const float* p_fwd, const float* dp,
-                                 const void* gates, float* d_out, float* dW1, float* db1, float* dw2, float* db2,
-                                 void* ws, size_t ws_bytes, int32_t precision, sgs_stream_t stream) {
   SGS_CHECK_ARG(n >= 0 && N > 0 && H > 0 && H % 4 == 0, "bad sizes (H must be a multiple of 4)");
-  SGS_CHECK_ARG(!gates || (edge_score_gate_bits_supported(H, precision) && ((uintptr_t)gates & 15) == 0),
-                "gate bits need H = 256, a 16-bit tensor-core precision and 16-byte alignment");
   if (n == 0) return SGS_OK;
   SGS_CHECK_ARG(out && src && dst && W1 && b1 && w2 && b2 && dp && d_out && dW1 && db1 && dw2 && db2 && ws,
                 "null pointer");
@@ -336,7 +308,7 @@ int32_t sgs_edge_score_bwd_gates(const float* out, int64_t N, int64_t H, const i
   if (tc_bwd_supported(precision, H)) {
     SGS_CHECK_ARG(p_fwd != nullptr, "tensor-core backward needs the forward probabilities p_fwd");
     return edge_score_bwd_tc(out, N, H, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, dw2,
-                             db2, reinterpret_cast<const uint32_t*>(gates), ws, ws_bytes, precision, st);
+                             db2, ws, ws_bytes, precision, st);
   }
   SGS_CHECK_ARG(precision == SGS_PREC_FP32 || precision == SGS_PREC_TF32 || is_16bit(precision), "unknown precision");
   // kind::tf32 needs 16-byte aligned rows; 16-bit modes at widths the fused kernels do not cover use fp32

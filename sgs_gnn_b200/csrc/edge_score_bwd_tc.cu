@@ -1,16 +1,10 @@
-// K1b tensor-core backward of the edge scorer: fused tcgen05 kernels around the 16-bit gate gradient G [q, H],
+// K1b tensor-core backward of the edge scorer: three fused tcgen05 kernels.  Nothing of size [q, 2H] is ever
+// written to HBM; the only intermediate is the 16-bit gate gradient G [q, H],
 //       G[e, j] = S * dz_e / (1 - p_drop) * [Z_ej + b1_j > 0] * keep_ej ,        dz = dp * p * (1 - p),
 // i.e. the hidden-layer gradient dA = G . diag(w2) WITHOUT its w2 factor.  That factor is folded into operands and
-// final epilogues, so no per-tile epilogue reduces anything across rows.
+// final epilogues, so no per-tile epilogue reduces anything across rows:
 //
-// H = 256 (BITS = true): G never exists in HBM.  The forward over all edges (edge_score_tc2.cu, WMASK) leaves 32
-// bytes of GATE BITS per edge, [Z_ej + b1_j > 0] * keep_ej; BF and BW rebuild their G tiles in shared memory from
-// those bits and the per-edge scalar S * dz_e / (1 - p_drop).  No recompute of Z, no [q, H] round trip (r01: a 6.9 ms
-// recompute kernel + 11.7 GB of G written once and read twice).  Without forward bits (two_pass pipeline, plain
-// autograd use) the pair kernel is run once on the bucketed edge list to produce them.
-// H = 128 (BITS = false): the r01 form -- BA below writes G to HBM, BF reads it by TMA, BW by loader threads.
-//
-//  BA  (H = 128 only)
+//  BA  (recompute; H = 256: the CTA-pair forward kernel in MODE 1, edge_score_tc2.cu; H = 128: the kernel below)
 //        MMA : Z  = F . W1^T ;   EPI : G -> HBM (16 bit), db2 += sum dz
 //  BF  (per 128-edge tile, per block of 128 node-embedding columns; diag(w2) . W1[:, cols] resident in smem and read
 //       as an MN-major operand -- the row-major bytes "transposed" by the descriptor):
@@ -33,30 +27,14 @@
 #include "tma.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
-#include <string.h>
 #include <type_traits>
 
 namespace sgs {
 
-int32_t edge_score_fwd_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
-                            const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                            const float* b2, float p_drop, uint64_t seed, float* p, uint32_t* mask,
-                            const int32_t* key_ids, cudaStream_t st);
-
-// One byte of gate bits (8 consecutive hidden units) -> the 16-byte operand chunk of G: 16-bit lanes of 0 / g.
-// nibble * 0x10204080 puts bit k of the nibble into the sign bit of byte k; PRMT with the selector's msb set
-// replicates that sign over a byte (twice per 16-bit lane).  gg = the row's 16-bit gradient in both halves.
-__device__ __forceinline__ uint32_t prmt_sign(uint32_t x, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(sel));
-  return r;
-}
-__device__ __forceinline__ uint4 expand_gate_byte(uint32_t byte, uint32_t gg) {
-  const uint32_t xl = (byte & 15u) * 0x10204080u;
-  const uint32_t xh = (byte >> 4) * 0x10204080u;
-  return make_uint4(prmt_sign(xl, 0x9988u) & gg, prmt_sign(xl, 0xBBAAu) & gg, prmt_sign(xh, 0x9988u) & gg,
-                    prmt_sign(xh, 0xBBAAu) & gg);
-}
+int32_t edge_score_bwd_gate_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, float p_drop,
+                                 uint64_t seed, const float* p_fwd, const float* dp, const float* dp_absmax,
+                                 void* g_out, float* db2, const int32_t* key_ids, cudaStream_t st);
 
 
 namespace kb {
@@ -361,16 +339,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 }
 
 // 18 warps = 5 on two of the four SM sub-partitions (16 K registers each): at most 96 registers per thread
-// BITS: the G tiles are generated in shared memory by warp 0 from the gate bits (gates [n, H / 32] uint32 in the
-// order of this edge list) and dz [n]; otherwise they are streamed from HBM by TMA (map_g).
-template <typename T, int H, bool BITS>
+template <typename T, int H>
 __global__ void __launch_bounds__(kbf::THREADS, 1)
 edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __restrict__ tab,
                          const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
                          const float* __restrict__ w2, const float* __restrict__ dp_absmax,
-                         float* __restrict__ d_out, const uint32_t* __restrict__ gates,
-                         const float* __restrict__ dz, float p_drop) {
+                         float* __restrict__ d_out) {
   using namespace kbf;
   using namespace tc;
   constexpr int NKIND = H / CB;
@@ -408,8 +383,7 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      // TMA: the producer's arrive.expect_tx, TMA completes the bytes; BITS: the 32 generating lanes arrive
-      mbar_init(full0 + 8 * s, BITS ? 32 : 1);
+      mbar_init(full0 + 8 * s, 1);       // the producer's arrive.expect_tx; TMA completes the bytes
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -456,45 +430,8 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
     // source differs from its predecessor's inside the same 64-edge half (the first edge of a half is never
     // flagged: the epilogue starts a fresh run there).  Dead edges (past n) become (0, 0): their G rows are zero.
     uint32_t it = 0, lt = 0;
-    const float gscale = BITS ? grad_scale(dp_absmax[0]) * (p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f) : 0.f;
     for (int64_t t = tile0; t < ntiles; t += tstep, ++lt) {
-      if (BITS) {
-        // lane l generates rows l, l + 32, l + 64, l + 96 of the tile: per row and sub-tile 16 bytes of gate bits
-        // -> 16 operand chunks (two [128 x 64] SWIZZLE_128B blocks); rows past n are exact zeros
-        uint32_t gg[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int64_t i = t * TILE_E + lane + 32 * k;
-          const float g = i < n ? dz[i] * gscale : 0.f;
-          gg[k] = Cvt<T>::pack(g, g);
-        }
-#pragma unroll 1
-        for (int js = 0; js < NJ; ++js, ++it) {
-          const uint32_t slot = it % NSTAGE;
-          uint4 m[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int64_t i = t * TILE_E + lane + 32 * k;
-            m[k] = make_uint4(0, 0, 0, 0);
-            if (i < n) m[k] = ld_stream_u4(reinterpret_cast<const uint4*>(gates + i * (H / 32)) + js);
-          }
-          mbar_wait(empty0 + 8 * slot, ((it / NSTAGE) & 1) ^ 1);
-          uint8_t* stage = sm + A_BYTES + slot * STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t r = lane + 32 * k;
-            const uint32_t w[4] = {m[k].x, m[k].y, m[k].z, m[k].w};
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const uint32_t byte = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
-              *reinterpret_cast<uint4*>(stage + (c >> 3) * (TILE_E * 128) + sw128_offset(r, c & 7)) =
-                  expand_gate_byte(byte, gg[k]);
-            }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(full0 + 8 * slot);
-        }
-      } else if (lane == 0) {
+      if (lane == 0) {
 #pragma unroll 1
         for (int js = 0; js < NJ; ++js, ++it) {
           const uint32_t slot = it % NSTAGE;
@@ -640,15 +577,13 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
 // =============================================================================================
 // BW: P[BN, 2H] = G^T . F over all edges of this CTA's tiles, g = column sums of G;  dW1, db1, dw2 from P and g
 // =============================================================================================
-// BITS: the dA (= G) sub-tiles are generated from the gate bits + dz instead of being read from HBM.
-template <typename T, int BN, int H, bool BITS>
+template <typename T, int BN, int H>
 __global__ void __launch_bounds__(kb::BW_THREADS, 1)
 edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                          const int32_t* __restrict__ ids, int64_t n, const T* __restrict__ dA,
                          const float* __restrict__ dp_absmax, const float* __restrict__ W1,
                          const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ dW1,
-                         float* __restrict__ db1, float* __restrict__ dw2, const uint32_t* __restrict__ gates,
-                         const float* __restrict__ dz, float p_drop) {
+                         float* __restrict__ db1, float* __restrict__ dw2) {
   using namespace kb;
   using namespace tc;
   constexpr int NB = H / BN;
@@ -739,8 +674,6 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
     float gs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) gs[k] = 0.f;
-    const float gscale = BITS ? grad_scale(dp_absmax[0]) * (p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f) : 0.f;
-    const uint8_t* gate_bytes = reinterpret_cast<const uint8_t*>(gates);
     // thread -> 16-byte chunk cc of the NIT consecutive rows NIT * (lt_id / CH) + k: consecutive edges mostly share
     // their source (runs of ~10 in bucket order), whose row chunk is then loaded once
     const int cc = lt_id % CH;
@@ -785,14 +718,7 @@ edge_score_bwd_dw_kernel(const T* __restrict__ tab, const int32_t* __restrict__ 
         const int item = lt_id + k * LOAD_THREADS;
         const int64_t i = s * SUB_M + item / (BN / 8);
         av[k] = make_uint4(0, 0, 0, 0);
-        if (BITS) {
-          if (i < n) {
-            const float g = dz[i] * gscale;
-            av[k] = expand_gate_byte(gate_bytes[i * (H / 8) + nb * (BN / 8) + item % (BN / 8)], Cvt<T>::pack(g, g));
-          }
-        } else if (i < n) {
-          av[k] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + i * H + nb * BN + (item % (BN / 8)) * 8));
-        }
+        if (i < n) av[k] = ld_stream_u4(reinterpret_cast<const uint4*>(dA + i * H + nb * BN + (item % (BN / 8)) * 8));
       }
       if (s + sstep < nsub) load_idx(s + sstep, sn2, dn2);
       const uint32_t slot = it % NSTAGE;
@@ -903,18 +829,13 @@ __global__ void bucket_key_kernel(const int32_t* __restrict__ dst, const int32_t
 }
 // in bucket order: ids_b[i'] = edge id (dropout mask key), its endpoints src_b / dst_b (so that no kernel chases
 // ids -> src/dst on its critical path) and dz_b[i'] = dp * p * (1 - p)
-// gates (nullable): the forward's gate bits, 32 bytes per edge of the FULL edge list -> gates_b in bucket order;
-// db2 (nullable): += sum dz (the epilogue of the r01 BA kernel did this)
 __global__ void bucket_gather_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ ids,
                                      const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                      const float* __restrict__ p_fwd, const float* __restrict__ dp, int64_t n,
                                      int32_t* __restrict__ ids_b, int32_t* __restrict__ src_b,
-                                     int32_t* __restrict__ dst_b, float* __restrict__ dz_b,
-                                     const uint4* __restrict__ gates, uint4* __restrict__ gates_b,
-                                     float* __restrict__ db2) {
+                                     int32_t* __restrict__ dst_b, float* __restrict__ dz_b) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  float acc = 0.f;
   for (; i < n; i += stride) {
     const int64_t o = pos ? pos[i] : i;
     const int64_t e = ids ? ids[o] : o;
@@ -922,17 +843,7 @@ __global__ void bucket_gather_kernel(const int32_t* __restrict__ pos, const int3
     src_b[i] = src[e];
     dst_b[i] = dst[e];
     const float pe = p_fwd[o];
-    const float dzv = dp[o] * pe * (1.0f - pe);
-    dz_b[i] = dzv;
-    acc += dzv;
-    if (gates) {
-      gates_b[2 * i] = gates[2 * e];
-      gates_b[2 * i + 1] = gates[2 * e + 1];
-    }
-  }
-  if (db2) {
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(db2, acc);
+    dz_b[i] = dp[o] * pe * (1.0f - pe);
   }
 }
 
@@ -950,10 +861,9 @@ static int bucket_shift(int64_t N, int64_t H) {
 // =============================================================================================
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t edge_score_bwd_tc_workspace_bytes(int64_t n, int64_t N, int64_t H) {
-  // absmax | tab [N,H] 16 bit | H = 128: G [n,H] 16 bit, H = 256: gate bits [n,H/8] in bucket order |
-  // ids_b, src_b, dst_b, dz_b, pos_a, pos_b [n] 32 bit | key_a, key_b [n] 8 bit | cub temp
-  const size_t per_edge = H == 256 ? (size_t)n * (H / 8) : (size_t)n * H * 2;
-  return 4096 + align256((size_t)N * H * 2) + align256(per_edge) + 6 * align256((size_t)n * 4) +
+  // absmax | tab [N,H] 16 bit | G [n,H] 16 bit | ids_b, src_b, dst_b, dz_b, pos_a, pos_b [n] 32 bit |
+  // key_a, key_b [n] 8 bit | cub temp
+  return 4096 + align256((size_t)N * H * 2) + align256((size_t)n * H * 2) + 6 * align256((size_t)n * 4) +
          2 * align256((size_t)n) + bucket_temp_bound(n);
 }
 
@@ -961,11 +871,9 @@ template <typename T, int H>
 static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const int32_t* dst, const int32_t* ids,
                           int64_t n, const float* W1, const float* b1, const float* w2, float p_drop, uint64_t seed,
                           const float* p_fwd, const float* dp, float* d_out, float* dW1, float* db1, float* dw2,
-                          float* db2, const uint32_t* gates, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          float* db2, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int BN = 128;
   constexpr int NB = H / BN;
-  constexpr bool BITS = H == 256;   // G tiles rebuilt from gate bits inside BF / BW
-  constexpr int is_bf16 = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   if (ws_bytes < edge_score_bwd_tc_workspace_bytes(n, N, H)) {
     set_error("sgs_edge_score_bwd: workspace too small");
     return SGS_E_WORKSPACE;
@@ -975,8 +883,7 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
   auto take = [&](size_t bytes) { uint8_t* p = cur; cur += align256(bytes); return p; };
   float* absmax = reinterpret_cast<float*>(take(256));
   T* tab = reinterpret_cast<T*>(take((size_t)N * H * 2));
-  T* dA = BITS ? nullptr : reinterpret_cast<T*>(take((size_t)n * H * 2));
-  uint32_t* gates_b = BITS ? reinterpret_cast<uint32_t*>(take((size_t)n * (H / 8))) : nullptr;
+  T* dA = reinterpret_cast<T*>(take((size_t)n * H * 2));
   int32_t* ids_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
   int32_t* src_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
   int32_t* dst_b = reinterpret_cast<int32_t*>(take((size_t)n * 4));
@@ -996,7 +903,7 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
   g = ceil_div(n8, 256);
   convert_rows_kernel_b<T><<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(out, n8, reinterpret_cast<uint4*>(tab));
   SGS_LAUNCH_CHECK();
-  // ---- destination-range bucketing: ids_b (bucket order, stable), dz_b, the forward's gate bits in that order ----
+  // ---- destination-range bucketing: ids_b (bucket order, stable), dz_b ----
   {
     const int shift = bucket_shift(N, H);
     const int nbuckets = (int)(((N - 1) >> shift) + 1);
@@ -1020,9 +927,7 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
       count_launch(2);
       pos = dv.Current();
     }
-    bucket_gather_kernel<<<eg, 256, 0, st>>>(pos, ids, src, dst, p_fwd, dp, n, ids_b, src_b, dst_b, dz_b,
-                                             BITS ? reinterpret_cast<const uint4*>(gates) : nullptr,
-                                             reinterpret_cast<uint4*>(gates_b), BITS ? db2 : nullptr);
+    bucket_gather_kernel<<<eg, 256, 0, st>>>(pos, ids, src, dst, p_fwd, dp, n, ids_b, src_b, dst_b, dz_b);
     SGS_LAUNCH_CHECK();
     // from here on the edge list is (src_b, dst_b) in bucket order, addressed directly
     src = src_b;
@@ -1037,14 +942,11 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     if (gr > items * kinds) gr = items * kinds;
     return (unsigned)gr;
   };
-  if (BITS) {
-    if (!gates) {
-      // no bits from a forward pass over these edges (two_pass pipeline, plain autograd use): one run of the pair
-      // kernel on the bucketed list writes them straight in bucket order (dropout keyed by the original ids)
-      const int32_t rc = edge_score_fwd_pair(tab, is_bf16, src, dst, nullptr, n, W1, b1, w2, b1 /* b2: unused */,
-                                             p_drop, seed, nullptr, gates_b, ids_b, st);
-      if (rc != SGS_OK) return rc;
-    }
+  if (H == 256 && n >= 2 * kb::TILE_M) {
+    // CTA pairs: every edge tile is gathered and built once (edge_score_tc2.cu, MODE 1)
+    const int32_t rc = edge_score_bwd_gate_pair(tab, std::is_same<T, __nv_bfloat16>::value ? 1 : 0, src, dst, ids, n,
+                                                W1, b1, p_drop, seed, p_fwd, dp, absmax, dA, db2, ids_b, st);
+    if (rc != SGS_OK) return rc;
   } else {
     auto kern = edge_score_bwd_da_kernel<T, BN, H>;
     constexpr size_t used = (size_t)2 * (H / 64) * BN * 128 + 3 * kb::STAGE_BYTES + BN * 8 + 16 * 8 + 16;
@@ -1055,10 +957,9 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     SGS_LAUNCH_CHECK();
   }
   {
-    auto kern = edge_score_bwd_df_kernel<T, H, BITS>;
+    auto kern = edge_score_bwd_df_kernel<T, H>;
     CUtensorMap map_g;
-    memset(&map_g, 0, sizeof(map_g));
-    if (!BITS && !make_map_16bit(&map_g, dA, n, H, H, kbf::TILE_E, is_bf16)) {
+    if (!make_map_16bit(&map_g, dA, n, H, H, kbf::TILE_E, std::is_same<T, __nv_bfloat16>::value)) {
       set_error("sgs_edge_score_bwd: cuTensorMapEncodeTiled failed");
       return SGS_E_CUDA;
     }
@@ -1067,18 +968,17 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
     static_assert(used <= 232448, "BF shared memory");
     const size_t smem = used + 1024 > 232448 ? 232448 : used + 1024;   // the kernel traps if its alignment pad does not fit
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(H / 128, ntiles), kbf::THREADS, smem, st>>>(map_g, tab, src, dst, ids, n, W1, w2, absmax, d_out,
-                                                                gates_b, dp, p_drop);
+    kern<<<grid_for(H / 128, ntiles), kbf::THREADS, smem, st>>>(map_g, tab, src, dst, ids, n, W1, w2, absmax, d_out);
     SGS_LAUNCH_CHECK();
   }
   {
-    auto kern = edge_score_bwd_dw_kernel<T, BN, H, BITS>;
+    auto kern = edge_score_bwd_dw_kernel<T, BN, H>;
     constexpr size_t stage = (size_t)64 * 2 * H * 2 + 64 * BN * 2;
     constexpr int nstage = (2 * stage + 4096 <= 232448) ? 2 : 1;
     const size_t smem = nstage * stage + 128 + BN * 4 + 1024;
     SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_for(NB, ceil_div(n, 64)), kb::BW_THREADS, smem, st>>>(tab, src, dst, ids, n, dA, absmax, W1, b1, w2,
-                                                                      dW1, db1, dw2, gates_b, dp, p_drop);
+                                                                      dW1, db1, dw2);
     SGS_LAUNCH_CHECK();
   }
   return SGS_OK;
@@ -1087,11 +987,11 @@ static int32_t launch_bwd(const float* out, int64_t N, const int32_t* src, const
 int32_t edge_score_bwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                           const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
                           float p_drop, uint64_t seed, const float* p_fwd, const float* dp, float* d_out, float* dW1,
-                          float* db1, float* dw2, float* db2, const uint32_t* gates, void* ws, size_t ws_bytes,
-                          int32_t precision, cudaStream_t st) {
+                          float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int32_t precision,
+                          cudaStream_t st) {
 #define SGS_KB(T, HH)                                                                                          \
   return launch_bwd<T, HH>(out, N, src, dst, ids, n, W1, b1, w2, p_drop, seed, p_fwd, dp, d_out, dW1, db1, dw2, \
-                           db2, gates, ws, ws_bytes, st)
+                           db2, ws, ws_bytes, st)
   if (precision == SGS_PREC_BF16) {
     if (H == 256) SGS_KB(__nv_bfloat16, 256);
     if (H == 128) SGS_KB(__nv_bfloat16, 128);

@@ -280,8 +280,7 @@ size_t edge_score_tc_workspace_bytes(int64_t n, int64_t N, int64_t H) {
 
 int32_t edge_score_fwd_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
                             const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                            const float* b2, float p_drop, uint64_t seed, float* p, uint32_t* mask,
-                            const int32_t* key_ids, cudaStream_t st);
+                            const float* b2, float p_drop, uint64_t seed, float* p, cudaStream_t st);
 
 // SGS_K1_SINGLE_CTA=1 selects the single-CTA kernel for H = 256 (A/B measurements)
 static bool use_cta_pairs() {
@@ -293,15 +292,10 @@ static bool use_cta_pairs() {
   return v == 1;
 }
 
-bool edge_score_gate_bits_supported(int64_t H, int32_t precision) {
-  return H == 256 && (precision == SGS_PREC_BF16 || precision == SGS_PREC_FP16) && use_cta_pairs();
-}
-
 template <typename T, int BN, int H>
 static int32_t launch_k1(const float* out, int64_t N, const int32_t* src, const int32_t* dst, const int32_t* ids,
                          int64_t n, const float* W1, const float* b1, const float* w2, const float* b2,
-                         float p_drop, uint64_t seed, float* p, uint32_t* mask, void* ws, size_t ws_bytes,
-                         cudaStream_t st) {
+                         float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int NB = H / BN;
   if (ws_bytes < edge_score_tc_workspace_bytes(n, N, H)) {
     set_error("sgs_edge_score_fwd: workspace too small");
@@ -316,12 +310,7 @@ static int32_t launch_k1(const float* out, int64_t N, const int32_t* src, const 
   SGS_LAUNCH_CHECK();
   if (H == 256 && use_cta_pairs()) {
     // CTA pairs (cta_group::2): every 128-edge tile is gathered and built once instead of once per W1 slice
-    return edge_score_fwd_pair(tab, Cvt<T>::kFmt == 1, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, mask,
-                               nullptr, st);
-  }
-  if (mask) {
-    set_error("sgs_edge_score_fwd: gate bits are produced by the CTA-pair kernel only (H = 256)");
-    return SGS_E_UNSUPPORTED;
+    return edge_score_fwd_pair(tab, Cvt<T>::kFmt == 1, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, st);
   }
   const size_t smem = k1_smem_bytes(BN, H);
   auto kern = edge_score_tc_kernel<T, BN, H>;
@@ -341,14 +330,14 @@ static int32_t launch_k1(const float* out, int64_t N, const int32_t* src, const 
 
 int32_t edge_score_fwd_tc(const float* out, int64_t N, int64_t H, const int32_t* src, const int32_t* dst,
                           const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                          const float* b2, float p_drop, uint64_t seed, float* p, uint32_t* mask, void* ws,
-                          size_t ws_bytes, int32_t precision, cudaStream_t st) {
+                          const float* b2, float p_drop, uint64_t seed, float* p, void* ws, size_t ws_bytes,
+                          int32_t precision, cudaStream_t st) {
   if (precision != SGS_PREC_BF16 && precision != SGS_PREC_FP16) {
     set_error("sgs_edge_score_fwd: tensor-core scorer supports bf16 / fp16 operands");
     return SGS_E_UNSUPPORTED;
   }
 #define SGS_K1(T, BN, HH) \
-  return launch_k1<T, BN, HH>(out, N, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, mask, ws, ws_bytes, st)
+  return launch_k1<T, BN, HH>(out, N, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, ws, ws_bytes, st)
   if (precision == SGS_PREC_BF16) {
     if (H == 256) SGS_K1(__nv_bfloat16, 128, 256);
     if (H == 128) SGS_K1(__nv_bfloat16, 128, 128);

@@ -52,20 +52,20 @@ constexpr int SMALL_BYTES = 2 * H * 4 + (3 * NSTAGE + 4) * 8 + 16;
 constexpr int USED_BYTES = B_BYTES + NSTAGE * STAGE_BYTES + SMALL_BYTES;
 }  // namespace k1p
 
-// Forward: p_out[i] = sigma(w2 . dropout(relu(Z + b1)) + b2)   (p_out may be NULL).
-// WMASK: the epilogue also writes the GATE BITS of every edge, mask_out[i, j / 32] bit (j % 32) =
-//         [Z_ij + b1_j > 0] * keep_ij  (H / 8 = 32 bytes per edge).  They are everything the backward needs from this
-//         pass: the 16-bit hidden-layer gate gradient  G[i, j] = S * dz_i / (1 - p_drop) * bit_ij  (dz = dp * p * (1 - p),
-//         S = grad_scale(max|dp|)) is regenerated from them inside the BF / BW kernels (edge_score_bwd_tc.cu), so the
-//         hybrid backward neither recomputes Z nor round-trips an [n, H] tensor through HBM (r01: the "BA" recompute
-//         kernel + 11.7 GB of G written once and read twice).
-template <typename T, bool WMASK>
+// MODE 0: forward, p_out[i] = sigma(w2 . dropout(relu(Z + b1)) + b2).
+// MODE 1: first backward kernel ("BA"): the same recompute of Z, but the epilogue writes the 16-bit hidden-layer
+//         gate gradient  G[i, j] = S * dz_i / (1 - p_drop) * [Z_ij + b1_j > 0] * keep_ij   (dz = dp * p * (1 - p),
+//         S = grad_scale(max|dp|)) to g_out [n, H] and accumulates db2 += sum_i dz_i.  The factor w2_j of
+//         dA = G . diag(w2) is folded into the operands / epilogues of the BF and BW kernels
+//         (edge_score_bwd_tc.cu), which also derive db1 and dw2 from G^T F -- this epilogue has no reductions.
+template <typename T, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k1p::THREADS, 1)
 edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                       const int32_t* __restrict__ ids, int64_t n, const float* __restrict__ W1,
                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                      float p_drop, uint64_t seed, float* __restrict__ p_out, uint32_t* __restrict__ mask_out,
-                      const int32_t* __restrict__ key_ids) {
+                      float p_drop, uint64_t seed, float* __restrict__ p_out, const float* __restrict__ p_fwd,
+                      const float* __restrict__ dp, const float* __restrict__ dp_absmax, T* __restrict__ g_out,
+                      float* __restrict__ db2, const int32_t* __restrict__ key_ids) {
   using namespace k1p;
   using namespace tc;
 
@@ -211,12 +211,15 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
     const int r = lg * 32 + lane;  // row of this CTA's tile == TMEM lane
     const uint32_t thr32 = dropout_threshold32(dropout_threshold(p_drop));
     const bool drop = p_drop > 0.f;
-    const float bias2 = b2[0];
+    const float bias2 = MODE == 0 ? b2[0] : 0.f;
+    const float gscale = MODE == 1 ? grad_scale(dp_absmax[0]) * (drop ? 1.0f / (1.0f - p_drop) : 1.0f) : 0.f;
+    float acc_b2 = 0.f;
     const uint32_t tempty_leader0 = mapa_shared(tempty0, 0);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16);
-    // the dropout key id of the NEXT tile's row is loaded one tile ahead: its latency (an HBM miss) would otherwise
-    // sit on the epilogue's critical path once per tile
+    // per-row inputs of the NEXT tile (dropout key id; MODE 1: dz, p) are loaded one tile ahead: their latency (an
+    // HBM miss each) would otherwise sit on the epilogue's critical path once per tile
     int64_t kid_n = 0;
+    float dz_n = 0.f, pe_n = 0.f;
     auto prefetch_row = [&](int64_t t) {
       const int64_t i = t * TILE_M + r;
       if (drop) {
@@ -224,6 +227,13 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
         if (key_ids) e = key_ids[e];   // the edge list was re-ordered by the caller: original ids for the mask
         else if (ids) e = ids[e];
         kid_n = e;
+      }
+      if (MODE == 1) {
+        dz_n = 0.f;
+        if (i < n) {
+          dz_n = dp[i];
+          if (p_fwd) pe_n = p_fwd[i];
+        }
       }
     };
     uint32_t lt = grp;
@@ -234,8 +244,18 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
       const uint32_t taddr = taddr0 + acc * H;
       const int64_t i = t * TILE_M + r;
       const int64_t kid = kid_n;
+      float dz = dz_n;
+      if (MODE == 1 && p_fwd) dz *= pe_n * (1.0f - pe_n);   // p_fwd == nullptr: dp already holds dz = dp * p * (1 - p)
       if (t + EPI_GROUPS * tstep < ntiles_padded) prefetch_row(t + EPI_GROUPS * tstep);
       const uint32_t rowkey = drop ? dropout_rowkey(seed, (uint64_t)kid) : 0u;
+      uint32_t g_lo = 0, g_hi = 0;   // MODE 1: this row's gate gradient in the low / high 16 bits
+      if (MODE == 1) {
+        acc_b2 += dz;
+        const float g = dz * gscale;
+        const uint32_t gg = Cvt<T>::pack(g, g);
+        g_lo = gg & 0xFFFFu;
+        g_hi = gg & 0xFFFF0000u;
+      }
       mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
       tc_fence_after();
       float z0 = 0.f, z1 = 0.f;
@@ -252,7 +272,33 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
         const uint32_t rk = rowkey ^ ((uint32_t)ch * 0x9E3779B9u);   // dropout_colmix: chunk part of the pair constant
         const float* bp = b1s + ch * 32;
         const float* wp = w2s + ch * 32;
-        uint32_t bits = 0;
+        if (MODE == 1) {
+          uint32_t o[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bp + j4 * 4);
+            bool m0 = __uint_as_float(v[j4 * 4 + 0]) + bb.x > 0.f;
+            bool m1 = __uint_as_float(v[j4 * 4 + 1]) + bb.y > 0.f;
+            bool m2 = __uint_as_float(v[j4 * 4 + 2]) + bb.z > 0.f;
+            bool m3 = __uint_as_float(v[j4 * 4 + 3]) + bb.w > 0.f;
+            if (drop) {
+              const uint32_t xa = rk ^ ((uint32_t)(2 * j4) * 0x7FEB352Du);
+              const uint32_t xb = rk ^ ((uint32_t)(2 * j4 + 1) * 0x7FEB352Du);
+              m0 = m0 && (xa * kDropMulEven >= thr32);
+              m1 = m1 && (xa * kDropMulOdd >= thr32);
+              m2 = m2 && (xb * kDropMulEven >= thr32);
+              m3 = m3 && (xb * kDropMulOdd >= thr32);
+            }
+            o[2 * j4] = (m0 ? g_lo : 0u) | (m1 ? g_hi : 0u);
+            o[2 * j4 + 1] = (m2 ? g_lo : 0u) | (m3 ? g_hi : 0u);
+          }
+          if (i < n) {
+            uint4* gp = reinterpret_cast<uint4*>(g_out + i * H + ch * 32);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) gp[c8] = make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 bb = *reinterpret_cast<const float4*>(bp + j4 * 4);
@@ -261,29 +307,26 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
           const float h1 = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bb.y, 0.f);
           const float h2 = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bb.z, 0.f);
           const float h3 = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bb.w, 0.f);
-          bool k0 = true, k1 = true, k2 = true, k3 = true;
           if (drop) {
             const uint32_t xa = rk ^ ((uint32_t)(2 * j4) * 0x7FEB352Du);
             const uint32_t xb = rk ^ ((uint32_t)(2 * j4 + 1) * 0x7FEB352Du);
-            k0 = xa * kDropMulEven >= thr32;
-            k1 = xa * kDropMulOdd >= thr32;
-            k2 = xb * kDropMulEven >= thr32;
-            k3 = xb * kDropMulOdd >= thr32;
-          }
-          if (k0) z0 = fmaf(ww.x, h0, z0);
-          if (k1) z1 = fmaf(ww.y, h1, z1);
-          if (k2) z0 = fmaf(ww.z, h2, z0);
-          if (k3) z1 = fmaf(ww.w, h3, z1);
-          if (WMASK) {
-            if (k0 && h0 > 0.f) bits |= 1u << (4 * j4 + 0);
-            if (k1 && h1 > 0.f) bits |= 1u << (4 * j4 + 1);
-            if (k2 && h2 > 0.f) bits |= 1u << (4 * j4 + 2);
-            if (k3 && h3 > 0.f) bits |= 1u << (4 * j4 + 3);
+            if (xa * kDropMulEven >= thr32) z0 = fmaf(ww.x, h0, z0);
+            if (xa * kDropMulOdd >= thr32) z1 = fmaf(ww.y, h1, z1);
+            if (xb * kDropMulEven >= thr32) z0 = fmaf(ww.z, h2, z0);
+            if (xb * kDropMulOdd >= thr32) z1 = fmaf(ww.w, h3, z1);
+          } else {
+            z0 = fmaf(ww.x, h0, z0);
+            z1 = fmaf(ww.y, h1, z1);
+            z0 = fmaf(ww.z, h2, z0);
+            z1 = fmaf(ww.w, h3, z1);
           }
         }
-        if (WMASK && i < n) mask_out[i * (H / 32) + ch] = bits;
       }
-      if (p_out && i < n) p_out[i] = 1.0f / (1.0f + expf(-(z0 + z1 + bias2)));
+      if (MODE == 0 && i < n) p_out[i] = 1.0f / (1.0f + expf(-(z0 + z1 + bias2)));
+    }
+    if (MODE == 1) {
+      acc_b2 = warp_sum(acc_b2);
+      if (lane == 0) atomicAdd(db2, acc_b2);
     }
   }
 
@@ -297,40 +340,47 @@ edge_score_tc2_kernel(const T* __restrict__ tab, const int32_t* __restrict__ src
 
 size_t edge_score_tc2_workspace_bytes(int64_t N) { return 1024 + (size_t)N * k1p::H * 2; }
 
-template <typename T, bool WMASK>
+template <typename T, int MODE>
 static int32_t launch_k1_pair(const T* tab, const int32_t* src, const int32_t* dst, const int32_t* ids, int64_t n,
                               const float* W1, const float* b1, const float* w2, const float* b2, float p_drop,
-                              uint64_t seed, float* p, uint32_t* mask, const int32_t* key_ids, cudaStream_t st) {
+                              uint64_t seed, float* p, cudaStream_t st, const float* p_fwd = nullptr,
+                              const float* dp = nullptr, const float* dp_absmax = nullptr, T* g_out = nullptr,
+                              float* db2 = nullptr, const int32_t* key_ids = nullptr) {
   size_t smem = (size_t)k1p::USED_BYTES + 1024;
   if (smem > 232448) smem = 232448;
-  auto kern = edge_score_tc2_kernel<T, WMASK>;
+  auto kern = edge_score_tc2_kernel<T, MODE>;
   SGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ndt = ceil_div(n, 2 * k1p::TILE_M);
   int64_t pairs = sm_count() / 2;
   if (pairs > ndt) pairs = ndt;
-  kern<<<(unsigned)(2 * pairs), k1p::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, mask,
-                                                          key_ids);
+  kern<<<(unsigned)(2 * pairs), k1p::THREADS, smem, st>>>(tab, src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p,
+                                                          p_fwd, dp, dp_absmax, g_out, db2, key_ids);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }
 
-// tab: the 16-bit node-embedding table [N, 256] (already converted).  p (nullable): probabilities; mask (nullable):
-// gate bits [n, 8] uint32 (see the kernel).  key_ids (nullable): original edge ids of a re-ordered edge list (the
-// dropout mask is keyed by them).
+// tab: the 16-bit node-embedding table [N, 256] (already converted)
 int32_t edge_score_fwd_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
                             const int32_t* ids, int64_t n, const float* W1, const float* b1, const float* w2,
-                            const float* b2, float p_drop, uint64_t seed, float* p, uint32_t* mask,
-                            const int32_t* key_ids, cudaStream_t st) {
-#define SGS_K1P(T, WM)                                                                                             \
-  return launch_k1_pair<T, WM>(reinterpret_cast<const T*>(tab), src, dst, ids, n, W1, b1, w2, b2, p_drop, seed, p, \
-                               mask, key_ids, st)
-  if (is_bf16) {
-    if (mask) SGS_K1P(__nv_bfloat16, true);
-    SGS_K1P(__nv_bfloat16, false);
-  }
-  if (mask) SGS_K1P(__half, true);
-  SGS_K1P(__half, false);
-#undef SGS_K1P
+                            const float* b2, float p_drop, uint64_t seed, float* p, cudaStream_t st) {
+  if (is_bf16)
+    return launch_k1_pair<__nv_bfloat16, 0>(reinterpret_cast<const __nv_bfloat16*>(tab), src, dst, ids, n, W1, b1, w2,
+                                            b2, p_drop, seed, p, st);
+  return launch_k1_pair<__half, 0>(reinterpret_cast<const __half*>(tab), src, dst, ids, n, W1, b1, w2, b2, p_drop,
+                                   seed, p, st);
+}
+
+// BA on CTA pairs (H = 256): g_out [n, 256] 16-bit gate gradients, db2 += sum dz.  tab / g_out: __half or bf16.
+int32_t edge_score_bwd_gate_pair(const void* tab, int32_t is_bf16, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ids, int64_t n, const float* W1, const float* b1, float p_drop,
+                                 uint64_t seed, const float* p_fwd, const float* dp, const float* dp_absmax,
+                                 void* g_out, float* db2, const int32_t* key_ids, cudaStream_t st) {
+  if (is_bf16)
+    return launch_k1_pair<__nv_bfloat16, 1>(reinterpret_cast<const __nv_bfloat16*>(tab), src, dst, ids, n, W1, b1, b1,
+                                            b1, p_drop, seed, nullptr, st, p_fwd, dp, dp_absmax,
+                                            reinterpret_cast<__nv_bfloat16*>(g_out), db2, key_ids);
+  return launch_k1_pair<__half, 1>(reinterpret_cast<const __half*>(tab), src, dst, ids, n, W1, b1, b1, b1, p_drop,
+                                   seed, nullptr, st, p_fwd, dp, dp_absmax, reinterpret_cast<__half*>(g_out), db2, key_ids);
 }
 
 }  // namespace sgs

@@ -50,13 +50,12 @@ class _EdgeProbBase(nn.Module):
     def _drop(self):
         return float(self.dropout.p) if self.training else 0.0
 
-    def score(self, out, graph, ids=None, precomputed=None, seed=None, precision=None, gates=None):
+    def score(self, out, graph, ids=None, precomputed=None, seed=None, precision=None):
         """_edge_score (model.py:115-122) on node embeddings `out` for all edges of `graph` or
-        the int32 id subset `ids`; returns [n] (not [n,1]).  `gates`: gate bits a no-grad forward over ALL edges of
-        `graph` left behind (ops.edge_score_forward(want_gates=True)), consumed by the backward."""
+        the int32 id subset `ids`; returns [n] (not [n,1])."""
         seed = ops.next_seed() if seed is None else seed
         return ops.edge_score(out, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, graph, ids,
-                              self._drop(), seed, precomputed, precision, gates)
+                              self._drop(), seed, precomputed, precision)
 
     def forward(self, node_features, edge_index, random_sampled_edge_index=None, use_checkpoint=False):
         profiler = getattr(self, "gpu_profiler", None)

@@ -671,35 +671,29 @@ def sage_conv(x, w_l, b_l, w_r, graph, relu=False, p_drop=0.0, seed=0):
 # edge scorer
 # ------------------------------------------------------------------------------------------
 
-def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0, precision=None, want_gates=False):
-    """p[n] for edges `ids` (int32) or all edges of `graph` (no autograd).
-    want_gates: also return the GATE BITS of these edges (uint8 [n, H/8]; sgs_edge_score_fwd_gates) -- what a later
-    backward over a subset of them needs instead of a recompute -- or None when the mode cannot produce them."""
+def edge_score_forward(out, graph, w1, b1, w2, b2, ids=None, p_drop=0.0, seed=0, precision=None):
+    """p[n] for edges `ids` (int32) or all edges of `graph` (no autograd)."""
     prec = _state["scorer"] if precision is None else precision
     out = _req(out, torch.float32, "out")
     n_nodes, h = out.shape
     n = graph.num_edges if ids is None else int(ids.numel())
     p = _vec(n, torch.float32, out.device)
-    gates = None
-    if want_gates and n > 0 and lib().sgs_edge_score_gate_bytes(n, h, prec) > 0:
-        gates = torch.empty(n, h // 8, dtype=torch.uint8, device=out.device)
     nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, prec, 0)
     ws = _ws(nbytes, out.device, "edge_score_fwd")
     with _timed("edge_score_fwd"):
-        check(lib().sgs_edge_score_fwd_gates(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
-                                             _p(b1), _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(gates),
-                                             _p(ws), ws.numel(), prec, _stream()), "sgs_edge_score_fwd")
-    return (p, gates) if want_gates else p
+        check(lib().sgs_edge_score_fwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
+                                       _p(b1), _p(w2), _p(b2), float(p_drop), int(seed), _p(p), _p(ws), ws.numel(),
+                                       prec, _stream()), "sgs_edge_score_fwd")
+    return p
 
 
 class EdgeScoreFn(torch.autograd.Function):
     """_edge_score (model.py:115-122) over all edges or an id subset.  `precomputed` lets the
     hybrid pipeline reuse the no-grad full-graph probabilities for the forward value while the
-    backward still runs (gradient) over just these edges; `gates` are the gate bits that forward left over ALL edges
-    of `graph` (the backward then needs no recompute of the hidden layer)."""
+    backward still runs (recompute + gradient) over just these edges."""
 
     @staticmethod
-    def forward(ctx, out, w1, b1, w2, b2, graph, ids, p_drop, seed, precomputed, precision, gates):
+    def forward(ctx, out, w1, b1, w2, b2, graph, ids, p_drop, seed, precomputed, precision):
         ctx.w2_shape, ctx.b2_shape = w2.shape, b2.shape
         w1 = _req(w1, torch.float32, "fc1.weight")
         b1 = _req(b1, torch.float32, "fc1.bias")
@@ -707,14 +701,11 @@ class EdgeScoreFn(torch.autograd.Function):
         b2 = _req(b2.reshape(-1), torch.float32, "fc2.bias")
         out = _req(out, torch.float32, "out")
         if precomputed is None:
-            # gate bits of exactly these edges: rows are indexed by position, so they only fit an ids-free backward
-            p, gates = edge_score_forward(out, graph, w1, b1, w2, b2, ids, p_drop, seed, precision,
-                                          want_gates=ids is None and any(ctx.needs_input_grad[:5]))
+            p = edge_score_forward(out, graph, w1, b1, w2, b2, ids, p_drop, seed, precision)
         else:
             p = precomputed
         ctx.graph, ctx.ids, ctx.p_drop, ctx.seed = graph, ids, p_drop, seed
         ctx.prec = _state["scorer"] if precision is None else precision
-        ctx.gates = gates
         ctx.save_for_backward(out, w1, b1, w2, b2, p)
         return p
 
@@ -731,24 +722,18 @@ class EdgeScoreFn(torch.autograd.Function):
         small = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
         nbytes = lib().sgs_edge_score_workspace_bytes(n, n_nodes, h, ctx.prec, 1)
         ws = _ws(nbytes, dev, "edge_score_bwd")
-        gates = ctx.gates
-        if gates is not None and lib().sgs_edge_score_gate_bytes(n, h, ctx.prec) == 0:
-            gates = None
         with _timed("edge_score_bwd"):
-            check(lib().sgs_edge_score_bwd_gates(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
-                                                 _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(p_fwd),
-                                                 _p(dp), _p(gates), _p(d_out), _p(dw1), _p(small), _p(small[h:]),
-                                                 _p(small[2 * h:]), _p(ws), ws.numel(), ctx.prec, _stream()),
-                  "sgs_edge_score_bwd")
-        ctx.gates = None
+            check(lib().sgs_edge_score_bwd(_p(out), n_nodes, h, _p(graph.src), _p(graph.dst), _p(ids), n, _p(w1),
+                                           _p(b1), _p(w2), _p(b2), float(ctx.p_drop), int(ctx.seed), _p(p_fwd),
+                                           _p(dp), _p(d_out), _p(dw1), _p(small), _p(small[h:]),
+                                           _p(small[2 * h:]), _p(ws), ws.numel(), ctx.prec, _stream()),
+                      "sgs_edge_score_bwd")
         db1, dw2, db2 = small[:h], small[h:2 * h].reshape(ctx.w2_shape), small[2 * h:].reshape(ctx.b2_shape)
-        return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+        return d_out, dw1, db1, dw2, db2, None, None, None, None, None, None
 
 
-def edge_score(out, w1, b1, w2, b2, graph, ids=None, p_drop=0.0, seed=0, precomputed=None, precision=None,
-               gates=None):
-    return EdgeScoreFn.apply(out, w1, b1, w2, b2, graph, ids, float(p_drop), int(seed), precomputed, precision,
-                             gates)
+def edge_score(out, w1, b1, w2, b2, graph, ids=None, p_drop=0.0, seed=0, precomputed=None, precision=None):
+    return EdgeScoreFn.apply(out, w1, b1, w2, b2, graph, ids, float(p_drop), int(seed), precomputed, precision)
 
 
 # ------------------------------------------------------------------------------------------

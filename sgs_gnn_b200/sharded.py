@@ -487,17 +487,17 @@ def learned_step(pipeline, args, epoch, max_epoch, model, sb, criterion, q, back
     p_drop = scorer._drop()
     fc1, fc2 = scorer.fc1, scorer.fc2
     with torch.no_grad():
-        p_loc, gates = ops.edge_score_forward(out.detach(), g_loc, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
-                                              fc2.bias.reshape(-1), None, p_drop, seed_sc, want_gates=True)
+        p_loc = ops.edge_score_forward(out.detach(), g_loc, fc1.weight, fc1.bias, fc2.weight.reshape(-1),
+                                       fc2.bias.reshape(-1), None, p_drop, seed_sc)
 
     smp = topq.select_ex(p_loc, sb.prob, draw_noise(), q, SAMPLE_TRAIN, coef, S=sampling._next_S(), gid=sb.gid)
     _check(smp.invalid, smp.n_global, q)
     lg_s = lg.subgraph(smp.sel)
     if pipeline == "hybrid":
         p_sel = ops.gather_selected(p_loc, None, smp.sel, SAMPLE_RAW, 0.0, None)[0]
-        p_s = scorer.score(out, g_loc, ids=smp.sel, precomputed=p_sel, seed=seed_sc, gates=gates)
+        p_s = scorer.score(out, g_loc, ids=smp.sel, precomputed=p_sel, seed=seed_sc)
     elif pipeline == "straight_through":
-        p_full_g = scorer.score(out, g_loc, precomputed=p_loc, seed=seed_sc, gates=gates)
+        p_full_g = scorer.score(out, g_loc, precomputed=p_loc, seed=seed_sc)
         p_s = ShardedStraightThroughFn.apply(p_full_g, sb.prob, smp.sel, smp.S, SAMPLE_TRAIN, coef, comm)
     else:
         raise ValueError(pipeline)

@@ -49,3 +49,14 @@ class FixtureBatch:
 @pytest.fixture(scope="session")
 def dev():
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _clean_injected_sampler_state():
+    """A failing test must not leave injected noise / normalisers behind for the next one."""
+    yield
+    try:
+        from sgs_gnn_b200 import sampling
+        sampling.clear_injected()
+    except Exception:
+        pass
