@@ -62,6 +62,14 @@ int32_t sgs_edge_index_split(const int64_t* edge_index, int64_t M, int64_t N, in
 int32_t sgs_edge_index_gather(const int64_t* edge_index, int64_t M, const int32_t* ids, int64_t q,
                               int64_t* out, int32_t* src_out, int32_t* dst_out, sgs_stream_t stream);
 
+/* The same two steps for an edge list that is ALREADY int32 (host batches narrowed before the upload: node ids fit
+ * 31 bits, int64 only doubles the PCIe bytes of training_hybrid.py:42's batch.to(device)): range check without a
+ * copy, and the gather of (src, dst)[ids] (int64 out optional). */
+int32_t sgs_edge_index_check32(const int32_t* src, const int32_t* dst, int64_t M, int64_t N, int32_t* err_flag,
+                               sgs_stream_t stream);
+int32_t sgs_edge_gather32(const int32_t* src, const int32_t* dst, const int32_t* ids, int64_t q, int64_t* out,
+                          int32_t* src_out, int32_t* dst_out, sgs_stream_t stream);
+
 size_t sgs_csr_workspace_bytes(int64_t M, int64_t N);
 /* Stable counting sort of the M edges by key (dst for the forward CSR, src for the backward
  * one): rowptr[N+1], perm[M] = edge ids in key order, nbr[M] = other[perm]; optional order[N+1]:

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import dist as sdist
+from . import loader as sloader
 from . import ops, sampling, sharded
 from .ops import SAMPLE_TRAIN
 
@@ -210,7 +211,8 @@ def train_epoch(pipeline, args, epoch, max_epoch, model, optimizer_gnn, optimize
         ops.seg_end(profiler, "backward")
 
     dp_mode = sdist.is_dist() and bool(getattr(args, "data_parallel", False)) and mode == "learned"
-    for batch in cluster_loader:
+    # host batches are uploaded one step ahead on a copy stream (loader.prefetch); device batches pass through
+    for batch in sloader.prefetch(cluster_loader, device):
         checks = []
         if dp_mode and not isinstance(batch, sharded.ShardedBatch):
             # data-parallel ranks must issue the same collectives: agree on the control flow of this iteration first

@@ -38,6 +38,36 @@ __global__ void edge_index_gather_kernel(const int64_t* __restrict__ ei, int64_t
   }
 }
 
+// the int32 form of an edge list (host batches narrowed by Batch.compact()): range check only, no copy
+__global__ void edge_index_check32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int64_t M,
+                                          int64_t N, int32_t* __restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < M; i += stride) {
+    const int64_t s = src[i], d = dst[i];
+    bad |= (s < 0) | (s >= N) | (d < 0) | (d >= N);
+  }
+  if (bad) *err = 1;
+}
+
+__global__ void edge_gather32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                     const int32_t* __restrict__ ids, int64_t q, int64_t* __restrict__ out,
+                                     int32_t* __restrict__ so, int32_t* __restrict__ dout) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < q; i += stride) {
+    const int64_t e = ids[i];
+    const int32_t s = src[e], d = dst[e];
+    if (out) {
+      out[i] = s;
+      out[q + i] = d;
+    }
+    if (so) so[i] = s;
+    if (dout) dout[i] = d;
+  }
+}
+
 __global__ void iota_copy_kernel(const int32_t* __restrict__ key, int64_t M, int32_t* __restrict__ kout,
                                  int32_t* __restrict__ vout) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,6 +171,26 @@ int32_t sgs_edge_index_gather(const int64_t* edge_index, int64_t M, const int32_
   SGS_CHECK_ARG(edge_index && ids, "null pointer");
   edge_index_gather_kernel<<<grid_for(q, 256), 256, 0, as_stream(stream)>>>(edge_index, M, ids, q, out,
                                                                             src_out, dst_out);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_edge_index_check32(const int32_t* src, const int32_t* dst, int64_t M, int64_t N, int32_t* err_flag,
+                               sgs_stream_t stream) {
+  SGS_CHECK_ARG(M >= 0 && N > 0, "bad sizes");
+  if (M == 0) return SGS_OK;
+  SGS_CHECK_ARG(src && dst && err_flag, "null pointer");
+  edge_index_check32_kernel<<<grid_for(M, 256), 256, 0, as_stream(stream)>>>(src, dst, M, N, err_flag);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_edge_gather32(const int32_t* src, const int32_t* dst, const int32_t* ids, int64_t q, int64_t* out,
+                          int32_t* src_out, int32_t* dst_out, sgs_stream_t stream) {
+  SGS_CHECK_ARG(q >= 0, "negative size");
+  if (q == 0) return SGS_OK;
+  SGS_CHECK_ARG(src && dst && ids, "null pointer");
+  edge_gather32_kernel<<<grid_for(q, 256), 256, 0, as_stream(stream)>>>(src, dst, ids, q, out, src_out, dst_out);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }

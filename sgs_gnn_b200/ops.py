@@ -251,6 +251,7 @@ class Graph:
         self._norm_unw = None
         self._norm_w = None  # (weakref to weight tensor, version, GcnNorm)
         self.oob_flag = None      # device int32 [1] set by sgs_edge_index_split when an id lies outside [0, N)
+        self._keep = None         # owner of src / dst when they are views (int32 edge_index given as such)
 
     def take_oob_flag(self):
         """The not-yet-checked out-of-range flag of this edge list (device int32 [1]) or None; the caller folds it
@@ -260,6 +261,24 @@ class Graph:
 
     @staticmethod
     def from_edge_index(edge_index, num_nodes, validate=False):
+        """edge_index: the reference's int64 [2, E] tensor, or the int32 [2, E] form of a compacted batch (its rows are
+        used as they are: no narrowing pass, half the bytes)."""
+        if isinstance(edge_index, torch.Tensor) and edge_index.dtype == torch.int32:
+            ei = _req(edge_index, torch.int32, "edge_index")
+            if ei.dim() != 2 or ei.size(0) != 2:
+                raise RuntimeError("edge_index must have shape [2, E]")
+            m = ei.size(1)
+            src, dst = ei[0], ei[1]
+            flag = torch.zeros(1, dtype=torch.int32, device=ei.device)
+            check(lib().sgs_edge_index_check32(_p(src), _p(dst), m, int(num_nodes), _p(flag), _stream()),
+                  "sgs_edge_index_check32")
+            if validate and int(flag.item()) != 0:
+                raise RuntimeError("edge_index contains node ids outside [0, num_nodes)")
+            g = Graph(src, dst, num_nodes, None)
+            g._keep = ei          # the rows are views of this tensor
+            if not validate:
+                g.oob_flag = flag
+            return g
         ei = _req(edge_index, torch.int64, "edge_index")
         if ei.dim() != 2 or ei.size(0) != 2:
             raise RuntimeError("edge_index must have shape [2, E]")
@@ -298,10 +317,8 @@ class Graph:
             check(lib().sgs_edge_index_gather(_p(self.edge_index), self.num_edges, _p(ids), q, _p(out), _p(src),
                                               _p(dst), _stream()), "sgs_edge_index_gather")
         else:
-            idl = ids.long()
-            src, dst = self.src[idl].contiguous(), self.dst[idl].contiguous()
-            if want_edge_index:
-                out = torch.stack([src.long(), dst.long()])
+            check(lib().sgs_edge_gather32(_p(self.src), _p(self.dst), _p(ids), q, _p(out), _p(src), _p(dst),
+                                          _stream()), "sgs_edge_gather32")
         g = Graph(src, dst, self.num_nodes, out)
         if ascending and self.src_sorted:
             g._src_sorted = True

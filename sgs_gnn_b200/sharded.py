@@ -269,6 +269,53 @@ class ShardedBatch:
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())
 
+    def compact(self):
+        """Host form with int32 edge_index (node ids fit 31 bits): half the PCIe bytes of the upload."""
+        if self.edge_index.dtype == torch.int32:
+            return self
+        return self._map_named(lambda k, t: t.to(torch.int32) if k == "edge_index" else t)
+
+    def _map_named(self, fn):
+        o = ShardedBatch(None, self.comm)
+        for k in self._TENSORS:
+            v = getattr(self, k, None)
+            setattr(o, k, fn(k, v) if v is not None else None)
+        o.num_classes, o.num_edges_global, o.bounds = self.num_classes, self.num_edges_global, self.bounds
+        o._sgs_has_train = self._sgs_has_train
+        return o
+
+    def upload_async(self, dev, stream):
+        """loader.prefetch: H2D copies of this rank's pieces on `stream`; of the replicated features only this rank's
+        1 / world row slice crosses PCIe (it lands in its slot of the full buffer, see finish_upload)."""
+        from .loader import copy_fields_async
+        w = self.comm.world if self.comm is not None else 1
+        n = self.x.size(0)
+        sliced = w > 1 and not self.comm.staged and n >= w
+        fields = {k: getattr(self, k, None) for k in self._TENSORS if not (sliced and k == "x")}
+        kw = copy_fields_async(fields, dev, stream)
+        o = self._map_named(lambda k, t: kw.get(k))
+        o._x_pending = None
+        if sliced:
+            chunk = (n + w - 1) // w
+            lo, hi = min(self.comm.rank * chunk, n), min((self.comm.rank + 1) * chunk, n)
+            full = torch.empty((w * chunk,) + tuple(self.x.shape[1:]), dtype=self.x.dtype, device=dev)
+            with torch.cuda.stream(stream):
+                full[self.comm.rank * chunk:self.comm.rank * chunk + (hi - lo)].copy_(self.x[lo:hi], non_blocking=True)
+            o._x_pending = (full, chunk, n)
+        return o
+
+    def finish_upload(self):
+        """On the consumer's stream, after the copies have landed: the NVLink all-gather of the feature slices."""
+        pend = getattr(self, "_x_pending", None)
+        if pend is not None:
+            full, chunk, n = pend
+            mine = full[self.comm.rank * chunk:(self.comm.rank + 1) * chunk]
+            with _timed("comm_exchange"):
+                dist.all_gather_into_tensor(full, mine.clone(), group=self.comm.group)
+            self.x = full[:n]
+            self._x_pending = None
+        return self
+
     def nbytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size()
                    for k in self._TENSORS if getattr(self, k, None) is not None)

@@ -130,3 +130,27 @@ def test_train_rejects_unknown_mode(dev):
     o = torch.optim.Adam(model.parameters())
     with pytest.raises(ValueError, match="Invalid mode"):
         training_hybrid.train(make_args(dev, mode="bogus"), 0, 1, model, o, o, o, nn.CrossEntropyLoss(), [b], q=10)
+
+
+def test_prefetched_int32_host_batches_match_resident_training(dev):
+    """loader.prefetch + Batch.compact(): a loader of pinned HOST batches with int32 edge_index (uploaded one step
+    ahead on a copy stream) must train exactly like the same batches resident on the device with int64 edge_index."""
+    from sgs_gnn_b200 import synth, training_hybrid, utils
+    from sgs_gnn_b200.model import GNNModel
+    b = synth.make_graph(None, seed=5, n=700, e=9000, f=24, c=4, homophily=0.8)
+    res = []
+    for mode in ("resident", "host"):
+        utils.fix_seeds(11)
+        model = GNNModel(24, 64, 4, 0.3, "GCN").to(dev)
+        og = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-2)
+        oe = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-2)
+        oa = torch.optim.Adam(model.parameters(), lr=1e-2)
+        batch = b.to(dev) if mode == "resident" else b.compact().pin_memory()
+        assert mode == "resident" or batch.edge_index.dtype == torch.int32
+        args = make_args(dev)
+        out = training_hybrid.train(args, 1, 30, model, og, oe, oa, nn.CrossEntropyLoss(), [batch] * 4, q=1800)
+        res.append((out, [p.detach().clone() for p in model.parameters()]))
+    assert res[0][0][2:] == res[1][0][2:]                       # same branch decisions
+    assert abs(res[0][0][0] - res[1][0][0]) < 1e-5 * max(1.0, abs(res[0][0][0]))
+    for pa, pb in zip(res[0][1], res[1][1]):
+        assert float((pa - pb).abs().max()) < 1e-5 * (1.0 + float(pa.abs().max()))
