@@ -134,6 +134,22 @@ int32_t sgs_table_f16(const float* in, int64_t N, int64_t D, int32_t scaled, voi
 int32_t sgs_spmm_h16(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
                      const float* dis, const float* loopw, const void* h16, const float* tscale, int64_t N, int64_t D,
                      const float* bias, float* out, int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream);
+/* Sharded form (one graph split by destination range over the GPUs): only rows [row_lo, row_hi) are
+ * computed; with peer_bases != NULL every finished row is ALSO stored into the same [N, D] buffer of every peer
+ * (peer_bases[g] + elem_off floats; bases of the ranks' symmetric arenas, mapped over NVLink) -- the slab all-gather
+ * of training_hybrid.py's GCN layers happens inside the SpMM epilogue.  h (fp32) or h16 + tscale (fp16 table). */
+int32_t sgs_spmm_sharded(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                         const float* dis, const float* loopw, const float* h, const void* h16, const float* tscale,
+                         int64_t N, int64_t D, const float* bias, float* out, int32_t flags, float p_drop,
+                         uint64_t seed, int64_t row_lo, int64_t row_hi, const uint64_t* peer_bases, int32_t world,
+                         int32_t rank, int64_t elem_off, sgs_stream_t stream);
+/* Slab exchange over peer memory (csrc/peer.cu): push_rows stores the local slab src[rows, D] (rows row0 .. of an
+ * [N, D] buffer) into every peer's buffer; reduce_rows sums the `world` copies of rows [row0, row0 + rows) with peer
+ * loads, in rank order.  The caller separates writers and readers with a cross-GPU barrier. */
+int32_t sgs_peer_push_rows(const float* src, const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t elem_off,
+                           int64_t row0, int64_t rows, int64_t D, int32_t include_self, sgs_stream_t stream);
+int32_t sgs_peer_reduce_rows(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t elem_off, int64_t row0,
+                             int64_t rows, int64_t D, float* out, sgs_stream_t stream);
 int32_t sgs_gcn_edge_grad_h16(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
                               const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
                               const int32_t* perm_src, const int32_t* src, const int32_t* dst, const float* G,

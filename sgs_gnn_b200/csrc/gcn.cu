@@ -10,6 +10,24 @@ namespace sgs {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlock = kWarpsPerBlock * 32;
 
+// Sharded SpMM (one graph split by destination range over the GPUs, peer.cu): only the rows [row_lo, row_hi) this
+// rank owns are computed, and every finished row is also stored into the same [N, D] buffer of every peer
+// (bases[g] + off floats: symmetric arena over NVLink) -- the slab all-gather happens inside the epilogue.
+struct SpmmPeers {
+  const uint64_t* bases;   // device array of `world` arena base addresses, or nullptr (no peer stores)
+  int world, rank;
+  int64_t off;             // element offset of the destination buffer inside every arena
+  int64_t row_lo, row_hi;  // owned row range
+};
+__device__ __forceinline__ void peer_store4(const SpmmPeers& pe, int64_t idx, const float4& v) {
+  for (int g = 0; g < pe.world; ++g)
+    if (g != pe.rank) reinterpret_cast<float4*>(pe.bases[g] + (uint64_t)(pe.off + idx) * sizeof(float))[0] = v;
+}
+__device__ __forceinline__ void peer_store1(const SpmmPeers& pe, int64_t idx, float v) {
+  for (int g = 0; g < pe.world; ++g)
+    if (g != pe.rank) reinterpret_cast<float*>(pe.bases[g] + (uint64_t)(pe.off + idx) * sizeof(float))[0] = v;
+}
+
 // ---------------------------------------------------------------------------------------
 // gcn_norm phase 1: weighted in-degree with "remaining" self loops.
 // ---------------------------------------------------------------------------------------
@@ -128,7 +146,7 @@ struct SpmmRow {
   __device__ __forceinline__ void finish(int64_t row, const float* __restrict__ dis, const float* __restrict__ loopw,
                                          const float* __restrict__ h, int D, int col0, int lane,
                                          const float* __restrict__ bias, float* __restrict__ out, int flags,
-                                         float scale, uint32_t thr, uint64_t seed) {
+                                         float scale, uint32_t thr, uint64_t seed, const SpmmPeers& pe) {
     float selfw = 0.f;
     if (dis) {
       const float d = dis[row];
@@ -160,9 +178,12 @@ struct SpmmRow {
           for (int t = 0; t < VEC; ++t) v[t] += orow[c + t];
         }
         if (VEC == 4) {
-          *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+          const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(orow + c) = o;
+          if (pe.bases) peer_store4(pe, row * D + c, o);
         } else {
           orow[c] = v[0];
+          if (pe.bases) peer_store1(pe, row * D + c, v[0]);
         }
       }
     }
@@ -175,7 +196,7 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
             const float* __restrict__ what, const float* __restrict__ dis,
             const float* __restrict__ loopw, const float* __restrict__ h, int64_t N, int D,
             const float* __restrict__ bias, float* __restrict__ out, int flags, float p_drop,
-            uint64_t seed, const int32_t* __restrict__ order) {
+            uint64_t seed, const int32_t* __restrict__ order, const SpmmPeers pe) {
   __shared__ float red[kWarpsPerBlock - 1][32 * VEC * K];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col0 = blockIdx.y * (32 * VEC * K);
@@ -187,6 +208,7 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
   // phase 1: hub rows, one block per row
   for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
     const int64_t row = order[hidx];
+    if (row < pe.row_lo || row >= pe.row_hi) continue;   // block-uniform
     r.clear();
     r.gather(nbr, what, h, D, col0, lane, rowptr[row], rowptr[row + 1], warp, kWarpsPerBlock);
     if (warp > 0) {
@@ -202,7 +224,7 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
         for (int k = 0; k < K; ++k)
 #pragma unroll
           for (int v = 0; v < VEC; ++v) r.acc[k][v] += red[w][(k * 32 + lane) * VEC + v];
-      r.finish(row, dis, loopw, h, D, col0, lane, bias, out, flags, scale, thr, seed);
+      r.finish(row, dis, loopw, h, D, col0, lane, bias, out, flags, scale, thr, seed, pe);
     }
     __syncthreads();
   }
@@ -213,9 +235,10 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
   const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
   for (; idx < N; idx += step) {
     const int64_t row = order ? order[idx] : idx;
+    if (row < pe.row_lo || row >= pe.row_hi) continue;
     r.clear();
     r.gather(nbr, what, h, D, col0, lane, rowptr[row], rowptr[row + 1], 0, 1);
-    r.finish(row, dis, loopw, h, D, col0, lane, bias, out, flags, scale, thr, seed);
+    r.finish(row, dis, loopw, h, D, col0, lane, bias, out, flags, scale, thr, seed, pe);
   }
 }
 
@@ -310,7 +333,7 @@ struct SpmmRowH {
   __device__ __forceinline__ void finish(int64_t row, const float* __restrict__ dis, const float* __restrict__ loopw,
                                          const __half* __restrict__ h, int D, int lane, float inv_scale,
                                          const float* __restrict__ bias, float* __restrict__ out, int flags,
-                                         float scale, uint32_t thr, uint64_t seed) {
+                                         float scale, uint32_t thr, uint64_t seed, const SpmmPeers& pe) {
     float selfw = 0.f;
     if (dis) {
       const float d = dis[row];
@@ -345,8 +368,13 @@ struct SpmmRowH {
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] += orow[c + t];
         }
-        *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(orow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        const float4 o0 = make_float4(v[0], v[1], v[2], v[3]), o1 = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4*>(orow + c) = o0;
+        *reinterpret_cast<float4*>(orow + c + 4) = o1;
+        if (pe.bases) {
+          peer_store4(pe, row * D + c, o0);
+          peer_store4(pe, row * D + c + 4, o1);
+        }
       }
     }
   }
@@ -357,7 +385,8 @@ __global__ void __launch_bounds__(kBlock)
 spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ what,
                 const float* __restrict__ dis, const float* __restrict__ loopw, const __half* __restrict__ h,
                 const float* __restrict__ tscale, int64_t N, int D, const float* __restrict__ bias,
-                float* __restrict__ out, int flags, float p_drop, uint64_t seed, const int32_t* __restrict__ order) {
+                float* __restrict__ out, int flags, float p_drop, uint64_t seed, const int32_t* __restrict__ order,
+                const SpmmPeers pe) {
   __shared__ float red[kWarpsPerBlock - 1][32 * 8 * K];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t thr = dropout_threshold(p_drop);
@@ -367,6 +396,7 @@ spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   SpmmRowH<K> r;
   for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
     const int64_t row = order[hidx];
+    if (row < pe.row_lo || row >= pe.row_hi) continue;   // block-uniform
     r.clear();
     r.gather(nbr, what, h, D, lane, rowptr[row], rowptr[row + 1], warp, kWarpsPerBlock);
     if (warp > 0) {
@@ -382,7 +412,7 @@ spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
         for (int k = 0; k < K; ++k)
 #pragma unroll
           for (int v = 0; v < 8; ++v) r.acc[k][v] += red[w][(k * 32 + lane) * 8 + v];
-      r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed);
+      r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed, pe);
     }
     __syncthreads();
   }
@@ -390,9 +420,10 @@ spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
   for (; idx < N; idx += step) {
     const int64_t row = order ? order[idx] : idx;
+    if (row < pe.row_lo || row >= pe.row_hi) continue;
     r.clear();
     r.gather(nbr, what, h, D, lane, rowptr[row], rowptr[row + 1], 0, 1);
-    r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed);
+    r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed, pe);
   }
 }
 
@@ -718,21 +749,29 @@ int32_t sgs_gcn_norm_apply(const int32_t* rowptr, const int32_t* perm, const int
   return SGS_OK;
 }
 
-int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order, const float* dis,
-                 const float* loopw, const float* h, int64_t N, int64_t D, const float* bias, float* out,
-                 int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream) {
-  SGS_CHECK_ARG(N > 0 && D > 0 && D < (1 << 20), "bad sizes");
-  SGS_CHECK_ARG(rowptr && h && out, "null pointer");
-  SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
+static int32_t spmm_impl(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                         const float* dis, const float* loopw, const float* h, const void* h16, const float* tscale,
+                         int64_t N, int64_t D, const float* bias, float* out, int32_t flags, float p_drop,
+                         uint64_t seed, const SpmmPeers& pe, cudaStream_t st) {
   if ((flags & SGS_SPMM_DROPOUT) && p_drop == 0.f) flags &= ~SGS_SPMM_DROPOUT;
-  cudaStream_t st = as_stream(stream);
-  const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)out) % 16 == 0);
+  if (h16) {
+    const __half* hh = reinterpret_cast<const __half*>(h16);
+    if (D <= 256)
+      spmm_h16_kernel<1><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias,
+                                                         out, flags, p_drop, seed, order, pe);
+    else
+      spmm_h16_kernel<2><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias,
+                                                         out, flags, p_drop, seed, order, pe);
+    SGS_LAUNCH_CHECK();
+    return SGS_OK;
+  }
+  const bool vec4 = (D % 4 == 0) && (((uintptr_t)h | (uintptr_t)out) % 16 == 0) && (pe.off % 4 == 0);
   dim3 block(kBlock);
 #define SGS_SPMM_LAUNCH(VEC, K)                                                                        \
   do {                                                                                                 \
     dim3 grid(row_grid(N), (unsigned)ceil_div(D, 32 * VEC * K));                                       \
     spmm_kernel<VEC, K><<<grid, block, 0, st>>>(rowptr, nbr, what, dis, loopw, h, N, (int)D, bias, out, \
-                                                flags, p_drop, seed, order);                           \
+                                                flags, p_drop, seed, order, pe);                       \
   } while (0)
   if (vec4) {
     if (D <= 128) SGS_SPMM_LAUNCH(4, 1);
@@ -746,6 +785,35 @@ int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, c
 #undef SGS_SPMM_LAUNCH
   SGS_LAUNCH_CHECK();
   return SGS_OK;
+}
+
+int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order, const float* dis,
+                 const float* loopw, const float* h, int64_t N, int64_t D, const float* bias, float* out,
+                 int32_t flags, float p_drop, uint64_t seed, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && D > 0 && D < (1 << 20), "bad sizes");
+  SGS_CHECK_ARG(rowptr && h && out, "null pointer");
+  SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
+  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N};
+  return spmm_impl(rowptr, nbr, what, order, dis, loopw, h, nullptr, nullptr, N, D, bias, out, flags, p_drop, seed, pe,
+                   as_stream(stream));
+}
+
+int32_t sgs_spmm_sharded(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                         const float* dis, const float* loopw, const float* h, const void* h16, const float* tscale,
+                         int64_t N, int64_t D, const float* bias, float* out, int32_t flags, float p_drop,
+                         uint64_t seed, int64_t row_lo, int64_t row_hi, const uint64_t* peer_bases, int32_t world,
+                         int32_t rank, int64_t elem_off, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && D > 0 && D < (1 << 20), "bad sizes");
+  SGS_CHECK_ARG(rowptr && out && (h || (h16 && tscale)), "null pointer");
+  SGS_CHECK_ARG(!h16 || (D % 8 == 0 && D <= 512 && (((uintptr_t)h16 | (uintptr_t)out) & 15) == 0),
+                "the fp16-table SpMM needs D % 8 == 0, D <= 512 and 16-byte alignment");
+  SGS_CHECK_ARG(0 <= row_lo && row_lo <= row_hi && row_hi <= N, "bad row range");
+  SGS_CHECK_ARG(!peer_bases || (world >= 1 && rank >= 0 && rank < world && elem_off >= 0), "bad peer arguments");
+  SGS_CHECK_ARG(!peer_bases || !h16 || elem_off % 4 == 0, "peer buffer offset must be a multiple of 4 floats");
+  SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
+  const SpmmPeers pe = {peer_bases, world, rank, elem_off, row_lo, row_hi};
+  return spmm_impl(rowptr, nbr, what, order, dis, loopw, h, h16, tscale, N, D, bias, out, flags, p_drop, seed, pe,
+                   as_stream(stream));
 }
 
 int32_t sgs_table_f16(const float* in, int64_t N, int64_t D, int32_t scaled, void* out16, float* tscale,
@@ -778,17 +846,9 @@ int32_t sgs_spmm_h16(const int32_t* rowptr, const int32_t* nbr, const float* wha
   SGS_CHECK_ARG(rowptr && h16 && tscale && out, "null pointer");
   SGS_CHECK_ARG((((uintptr_t)h16 | (uintptr_t)out) & 15) == 0, "h16 / out must be 16-byte aligned");
   SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
-  if ((flags & SGS_SPMM_DROPOUT) && p_drop == 0.f) flags &= ~SGS_SPMM_DROPOUT;
-  cudaStream_t st = as_stream(stream);
-  const __half* hh = reinterpret_cast<const __half*>(h16);
-  if (D <= 256)
-    spmm_h16_kernel<1><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias, out,
-                                                       flags, p_drop, seed, order);
-  else
-    spmm_h16_kernel<2><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias, out,
-                                                       flags, p_drop, seed, order);
-  SGS_LAUNCH_CHECK();
-  return SGS_OK;
+  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N};
+  return spmm_impl(rowptr, nbr, what, order, dis, loopw, nullptr, h16, tscale, N, D, bias, out, flags, p_drop, seed,
+                   pe, as_stream(stream));
 }
 
 int32_t sgs_act_bwd(const float* gout, const float* out, int64_t n, float scale, float* gin,

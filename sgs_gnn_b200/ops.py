@@ -512,25 +512,41 @@ def gather_table(h, scaled=False):
 
 
 def spmm(csr, what, norm, h, bias=None, relu=False, p_drop=0.0, seed=0, out=None, accumulate=False, add_root=False,
-         table=None):
+         table=None, rows=None, peers=None):
     """K3b.  `table`: the GatherTable of `h` (fp16 gather mode) -- the neighbour rows and the self term then come
-    from it instead of from `h`."""
+    from it instead of from `h`.  Sharded form: `rows` = (lo, hi) computes only these rows; `peers` = (comm, (stage
+    view, elem_off)) also stores every finished row into the stage of every peer GPU (sgs_spmm_sharded)."""
     rowptr, _perm, nbr, order = csr
     n, d = h.shape
     if out is None:
         out = torch.empty(n, d, dtype=torch.float32, device=h.device)
     flags = ((SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0) | (SPMM_ACCUM if accumulate else 0) |
              (SPMM_ADD_ROOT if add_root else 0))
+    dis = _p(norm.dis) if norm is not None else None
+    loopw = _p(norm.loopw) if norm is not None else None
+    if rows is not None or peers is not None:
+        lo, hi = rows if rows is not None else (0, n)
+        bases, world, rank, off = None, 1, 0, 0
+        if peers is not None:
+            comm, (_st, off) = peers
+            bases, world, rank = comm.peer.bases, comm.world, comm.rank
+        with _timed(f"spmm_d{d}"):
+            check(lib().sgs_spmm_sharded(_p(rowptr), _p(nbr), _p(what), _p(order), dis, loopw,
+                                         None if table is not None else _p(h),
+                                         _p(table.data) if table is not None else None,
+                                         _p(table.scale) if table is not None else None, n, d, _p(bias), _p(out),
+                                         flags, float(p_drop), int(seed), int(lo), int(hi), bases, world, rank,
+                                         int(off), _stream()), "sgs_spmm_sharded")
+        return out
     if table is not None:
         with _timed(f"spmm_d{d}"):
-            check(lib().sgs_spmm_h16(_p(rowptr), _p(nbr), _p(what), _p(order), _p(norm.dis) if norm is not None else None,
-                                     _p(norm.loopw) if norm is not None else None, _p(table.data), _p(table.scale), n,
-                                     d, _p(bias), _p(out), flags, float(p_drop), int(seed), _stream()), "sgs_spmm_h16")
+            check(lib().sgs_spmm_h16(_p(rowptr), _p(nbr), _p(what), _p(order), dis, loopw, _p(table.data),
+                                     _p(table.scale), n, d, _p(bias), _p(out), flags, float(p_drop), int(seed),
+                                     _stream()), "sgs_spmm_h16")
         return out
     with _timed(f"spmm_d{d}"):
-        check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(order), _p(norm.dis) if norm is not None else None,
-                             _p(norm.loopw) if norm is not None else None, _p(h), n, d, _p(bias), _p(out), flags,
-                             float(p_drop), int(seed), _stream()), "sgs_spmm")
+        check(lib().sgs_spmm(_p(rowptr), _p(nbr), _p(what), _p(order), dis, loopw, _p(h), n, d, _p(bias), _p(out),
+                             flags, float(p_drop), int(seed), _stream()), "sgs_spmm")
     return out
 
 

@@ -39,9 +39,52 @@ from .ops import _p, _req, _stream, _timed
 # collectives over row slabs
 # ------------------------------------------------------------------------------------------
 
+class PeerArena:
+    """The symmetric arena of csrc/peer.cu (torch.distributed._symmetric_memory is the plumbing: same-size buffers on
+    every GPU, all mapped into every process, plus a cross-GPU barrier on the stream).  Four [N, D]-sized regions:
+    two alternating STAGES (destinations of the producers' peer stores of a slab all-gather) and two alternating
+    PARTIALS (sources of the peer loads of a slab reduce-scatter).  Alternation makes ONE barrier per exchange enough:
+    a region is rewritten two exchanges later, by when every rank has passed a barrier it could only reach after it
+    had finished reading the region (single stream, program order)."""
+
+    def __init__(self, comm, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._sm = symm_mem
+        self.comm = comm
+        self.device = device
+        self.cap = 0
+        self.arena = self.hdl = None
+        self._flip = {"stage": 0, "part": 0}
+
+    def _ensure(self, nfloats):
+        need = (int(nfloats) + 1023) // 1024 * 1024
+        if need <= self.cap:
+            return
+        # collective (every rank asks for the same global [N, D] sizes in the same order)
+        self.cap = need
+        self.arena = self._sm.empty(4 * need, dtype=torch.float32, device=self.device)
+        group = self.comm.group if self.comm.group is not None else dist.group.WORLD
+        self.hdl = self._sm.rendezvous(self.arena, group)
+        self.bases = self.hdl.buffer_ptrs_dev
+        self.hdl.barrier(channel=0)
+
+    def region(self, kind, n, d):
+        """(tensor view [n, d] of the local arena, element offset) of the next `kind` region."""
+        self._ensure(n * d)
+        k = self._flip[kind]
+        self._flip[kind] = k ^ 1
+        off = ((0 if kind == "stage" else 2) + k) * self.cap
+        return self.arena[off:off + n * d].view(n, d), off
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
 class Comm:
-    """Row-slab collectives on top of torch.distributed (NCCL over NVLink on the GPU box; gloo,
-    staged through host memory, in the tests)."""
+    """Row-slab collectives.  On the GPU box (NCCL backend) the slab all-gathers / reduce-scatters of the sharded
+    GCN layers run over NVLink PEER MEMORY with hand-written kernels (csrc/peer.cu, the SpMM epilogue's peer stores);
+    NCCL keeps the small scalar / histogram / weight-gradient all-reduces.  In the tests (gloo) everything is staged
+    through host memory."""
 
     def __init__(self, group=None):
         self.group = group
@@ -53,6 +96,47 @@ class Comm:
             self.world, self.rank, self.backend = 1, 0, "none"
         self.staged = self.backend == "gloo"
         self.uneven_native = os.environ.get("SGS_SHARD_UNEVEN", "native") == "native"
+        self.peer = None
+        if self.world > 1 and self.backend == "nccl" and os.environ.get("SGS_PEER", "1") != "0":
+            self.peer = PeerArena(self, torch.device("cuda", torch.cuda.current_device()))
+
+    # ---- peer-memory slab exchange ----
+    def peer_stage(self, n, d):
+        """Destination of a fused slab all-gather: (stage view, elem_off) or None when peer memory is not in use
+        (d % 4 != 0 rows cannot be moved as float4)."""
+        if self.peer is None or (n * d) % 4 or d % 4:
+            return None
+        return self.peer.region("stage", n, d)
+
+    def peer_finish_exchange(self, full, bounds, stage, pushed):
+        """Second half of a slab all-gather over peer memory.  pushed: the producer already stored this rank's rows
+        into the peers' stages (SpMM epilogue); otherwise they are pushed here.  Then: barrier, copy the foreign rows
+        out of the local stage."""
+        st, off = stage
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        d = full.size(1)
+        with _timed("comm_exchange"):
+            if not pushed and hi > lo:
+                check(lib().sgs_peer_push_rows(_p(full[lo:hi]), self.peer.bases, self.world, self.rank, off, lo,
+                                               hi - lo, d, 0, _stream()), "sgs_peer_push_rows")
+            self.peer.barrier()
+            if lo > 0:
+                full[:lo].copy_(st[:lo])
+            if hi < full.size(0):
+                full[hi:].copy_(st[hi:])
+        return full
+
+    def peer_reduce_rows(self, part, off, bounds):
+        """Sum over ranks of the partial [N, D] every rank left in its PARTIAL region -> this rank's owned rows."""
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        d = part.size(1)
+        out = torch.empty(hi - lo, d, dtype=torch.float32, device=part.device)
+        with _timed("comm_reduce"):
+            self.peer.barrier()
+            if hi > lo:
+                check(lib().sgs_peer_reduce_rows(self.peer.bases, self.world, self.rank, off, lo, hi - lo, d, _p(out),
+                                                 _stream()), "sgs_peer_reduce_rows")
+        return out
 
     def all_reduce(self, t):
         if self.world == 1:
@@ -70,6 +154,10 @@ class Comm:
         """In place: afterwards every rank's owned row slab of `full` holds its owner's values."""
         if self.world == 1:
             return full
+        if full.dim() == 2 and full.dtype == torch.float32 and full.is_contiguous():
+            stage = self.peer_stage(full.size(0), full.size(1))
+            if stage is not None:
+                return self.peer_finish_exchange(full, bounds, stage, pushed=False)
         sizes = [bounds[i + 1] - bounds[i] for i in range(self.world)]
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         even = len(set(sizes)) == 1
@@ -85,7 +173,7 @@ class Comm:
                     if r != self.rank and sizes[r] > 0:
                         full[bounds[r]:bounds[r + 1]].copy_(outs[r][: sizes[r]])
             elif even:
-                dist.all_gather_into_tensor(full, full[lo:hi].clone(), group=self.group)
+                dist.all_gather_into_tensor(full, full[lo:hi], group=self.group)     # in place: no staging copy
             else:
                 dist.all_gather(list(full.split(sizes)), full[lo:hi].clone(), group=self.group)
         return full
@@ -113,6 +201,11 @@ class Comm:
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         if self.world == 1:
             return full[lo:hi]
+        if (self.peer is not None and full.dim() == 2 and full.dtype == torch.float32 and full.size(1) % 4 == 0):
+            part, off = self.peer.region("part", full.size(0), full.size(1))
+            with _timed("comm_reduce"):
+                part.copy_(full)
+            return self.peer_reduce_rows(part, off, bounds)
         sizes = [bounds[i + 1] - bounds[i] for i in range(self.world)]
         even = len(set(sizes)) == 1
         with _timed("comm_reduce"):
@@ -362,8 +455,12 @@ class ShardedGCNConvFn(torch.autograd.Function):
             if hi > lo:
                 ops.linear_nt_into(x[lo:hi], weight, h[lo:hi])
             lg.comm.exchange_rows(h, lg.bounds)
-        out = ops.spmm(g.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed, table=ops.gather_table(h))
-        if exchange_out:
+        stage = lg.comm.peer_stage(n, d) if (exchange_out and lg.comm.world > 1) else None
+        out = ops.spmm(g.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed, table=ops.gather_table(h),
+                       rows=(lo, hi), peers=(lg.comm, stage) if stage is not None else None)
+        if stage is not None:
+            lg.comm.peer_finish_exchange(out, lg.bounds, stage, pushed=True)
+        elif exchange_out:
             lg.comm.exchange_rows(out, lg.bounds)
         ctx.lg, ctx.norm, ctx.relu, ctx.p_drop, ctx.exchange_out = lg, norm, relu, p_drop, exchange_out
         ctx.has_w = edge_weight is not None
@@ -396,9 +493,15 @@ class ShardedGCNConvFn(torch.autograd.Function):
             if ns > 0:
                 check(lib().sgs_colsum(_p(g_full[lo:hi]), ns, d, _p(db), _stream()), "sgs_colsum")
         if need_w or need_x:
-            dh = ops.spmm(g.csr_src, norm.what_src, norm, g_full,      # partial sums for arbitrary rows
-                          table=ops.gather_table(g_full, scaled=True))
-            dh_slab = comm.reduce_rows(dh, bounds)
+            tab_g = ops.gather_table(g_full, scaled=True)
+            if comm.peer is not None and d % 4 == 0 and comm.world > 1:
+                # partial sums for arbitrary rows, left in the symmetric arena and summed with peer loads
+                part, off = comm.peer.region("part", n, d)
+                ops.spmm(g.csr_src, norm.what_src, norm, g_full, table=tab_g, out=part)
+                dh_slab = comm.peer_reduce_rows(part, off, bounds)
+            else:
+                dh = ops.spmm(g.csr_src, norm.what_src, norm, g_full, table=tab_g)
+                dh_slab = comm.reduce_rows(dh, bounds)
             if need_w:
                 dw = torch.zeros_like(weight)
                 if ns > 0:

@@ -1,6 +1,8 @@
-"""Worker of tests/test_gpu_sharded.py: one process per emulated rank (gloo rendezvous, every rank on
-cuda:0 -- collectives are host-side, no kernel waits on another process).  Checks that the
-destination-sharded learned step reproduces the single-GPU step on the same graph."""
+"""Worker of tests/test_gpu_sharded.py: one process per rank.  Default: gloo rendezvous, every rank on cuda:0
+(collectives are host-side, no kernel waits on another process) -- runs on a one-GPU box.  SGS_TEST_BACKEND=nccl: one
+GPU per rank over NCCL, which also exercises the peer-memory slab exchange (csrc/peer.cu, the SpMM epilogue's peer
+stores) -- needs as many GPUs as ranks.  Checks that the destination-sharded learned step reproduces the single-GPU
+step on the same graph."""
 import os
 import sys
 from types import SimpleNamespace
@@ -23,13 +25,18 @@ def make_args(dev, conditional, pipeline):
 def run(rank, world, port, pipeline, conditional, edge_mlp, n, e, f, c, hdim):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    backend = os.environ.get("SGS_TEST_BACKEND", "gloo")
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import extended as ox
         from sgs_gnn_b200 import _train_core, ops, sampling, sharded, synth
         from sgs_gnn_b200 import dist as sdist
         from sgs_gnn_b200.model import GNNModel
-        dev = torch.device("cuda:0")
+        dev = torch.device("cuda", rank) if backend == "nccl" else torch.device("cuda:0")
         ops.set_precision(gemm="fp32", scorer="fp32")
         b = synth.make_graph(None, seed=11, n=n, e=e, f=f, c=c).to(dev)
         q = int(b.num_edges * 0.25)
@@ -59,6 +66,8 @@ def run(rank, world, port, pipeline, conditional, edge_mlp, n, e, f, c, hdim):
             dist.all_gather_object(parts, mine.tolist())
             got = sorted(i for p_ in parts for i in p_)
             assert got == want.sel.cpu().tolist(), f"trial {trial}: sharded selection differs"
+        if rank == 0 and backend == "nccl":
+            print(f"peer-memory slab exchange: {'on' if comm.peer is not None else 'OFF'}", flush=True)
             assert r.n_global == q
 
         # ---- one learned step: single GPU vs sharded ----

@@ -22,13 +22,14 @@ def _free_port():
     return p
 
 
-def _launch(world, pipeline, conditional, edge_mlp="GCN", shape=(600, 9000, 24, 5, 32)):
+def _launch(world, pipeline, conditional, edge_mlp="GCN", shape=(600, 9000, 24, 5, 32), backend="gloo"):
     port = _free_port()
     procs = []
+    env = dict(os.environ, SGS_TEST_BACKEND=backend)
     for r in range(world):
         cmd = [sys.executable, os.path.join(HERE, "_sharded_worker.py"), str(r), str(world), str(port), pipeline,
                "1" if conditional else "0", edge_mlp] + [str(v) for v in shape]
-        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
     outs = []
     for p in procs:
         try:
@@ -55,3 +56,16 @@ def test_sharded_step_matches_single_gpu(dev, world, pipeline, conditional):
 def test_sharded_step_mlp_scorer(dev):
     out = _launch(2, "hybrid", False, edge_mlp="MLP")
     assert "max rel grad err" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pipeline,conditional", [("hybrid", True), ("straight_through", False)])
+def test_sharded_step_over_nccl_and_peer_memory(dev, pipeline, conditional):
+    """One GPU per rank over NCCL: the slab all-gathers / reduce-scatters run over NVLink peer memory (the SpMM
+    epilogue's peer stores, push / reduce kernels of csrc/peer.cu).  Needs >= 2 GPUs (skipped on a one-GPU box; run on
+    the 2-GPU box, output kept in profiles/r02_sharded_nccl_test.log)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _launch(2, pipeline, conditional, shape=(2000, 40000, 24, 5, 64), backend="nccl")
+    assert "max rel grad err" in out and "peer-memory slab exchange: on" in out
