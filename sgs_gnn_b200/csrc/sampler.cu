@@ -452,12 +452,17 @@ topq_scan_kernel(int* __restrict__ blk_gt, int* __restrict__ blk_eq, int nb) {
   }
 }
 
+// The selected ids of a chunk are first compacted into shared memory (block-local output order) and then copied out
+// with coalesced 4-byte stores: ncu r01 showed the direct form -- every thread storing its ~1.6 selected ids one
+// predicated STG at a time -- at 19 % of DRAM bandwidth, 0.32 ms per draw.
 __global__ void __launch_bounds__(kChunkThreads)
 topq_write_kernel(const uint32_t* __restrict__ keys, int64_t E, const long long* __restrict__ state,
                   long long tie_skip, const int* __restrict__ blk_gt, const int* __restrict__ blk_eq,
                   int32_t* __restrict__ sel, int64_t q_cap, uint8_t* __restrict__ mask,
                   long long* __restrict__ n_sel_out) {
   __shared__ int wg[32], we[32];
+  __shared__ int tot_g, tot_e;
+  __shared__ int32_t stage[kChunk];
   const uint32_t tau = (uint32_t)state[2];
   long long avail = state[4] - tie_skip;  // ties this shard may still take
   if (avail < 0) avail = 0;
@@ -493,43 +498,27 @@ topq_write_kernel(const uint32_t* __restrict__ keys, int64_t E, const long long*
     }
     wg[lane] = ia - a;
     we[lane] = ib - b;
+    if (lane == 31) { tot_g = ia; tot_e = ib; }
   }
   __syncthreads();
-  long long g_before = (long long)blk_gt[blockIdx.x] + wg[wid] + (ig - gt);
-  long long e_before = (long long)blk_eq[blockIdx.x] + we[wid] + (ie - eq);
+  const long long bg = blk_gt[blockIdx.x], be = blk_eq[blockIdx.x];
+  const long long be_taken = be < avail ? be : avail;        // ties taken before this chunk
+  const long long pos_block0 = bg + be_taken;                // output position of the chunk's first selected id
+  long long g_before = bg + wg[wid] + (ig - gt);
+  long long e_before = be + we[wid] + (ie - eq);
   uint64_t mbits = 0;
-  if (eq == 0) {
-    // fast path (no threshold tie among this thread's keys -- ties are a handful per 10^8 keys): the output
-    // position advances by one per selected key; 32-bit arithmetic on a per-thread base pointer
-    const long long pos0 = g_before + (e_before < avail ? e_before : avail);
-    long long room = q_cap - pos0;
-    int lim = sel ? (room > 8 ? 8 : (room < 0 ? 0 : (int)room)) : 0;
-    int32_t* out = sel ? sel + pos0 : nullptr;
-    int n_out = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (base + j < E && k[j] > tau) {
-        if (n_out < lim) out[n_out] = (int32_t)(base + j);
-        ++n_out;
-        mbits |= (uint64_t)1 << (8 * j);
-      }
+  for (int j = 0; j < 8; ++j) {
+    const bool in = base + j < E;
+    const bool is_gt = in && (k[j] > tau);
+    const bool is_eq = in && (k[j] == tau);
+    if (is_gt || (is_eq && e_before < avail)) {
+      const long long pos = g_before + (e_before < avail ? e_before : avail);
+      stage[(int)(pos - pos_block0)] = (int32_t)(base + j);
+      mbits |= (uint64_t)1 << (8 * j);
     }
-    g_before += gt;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const bool in = base + j < E;
-      const bool is_gt = in && (k[j] > tau);
-      const bool is_eq = in && (k[j] == tau);
-      const bool take = is_gt || (is_eq && e_before < avail);
-      if (take) {
-        const long long pos = g_before + (e_before < avail ? e_before : avail);
-        if (sel && pos < q_cap) sel[pos] = (int32_t)(base + j);
-        mbits |= (uint64_t)1 << (8 * j);
-      }
-      g_before += is_gt;
-      e_before += is_eq;
-    }
+    g_before += is_gt;
+    e_before += is_eq;
   }
   if (mask) {
     if (base + 8 <= E && ((uintptr_t)(mask + base) & 7) == 0) {
@@ -540,8 +529,14 @@ topq_write_kernel(const uint32_t* __restrict__ keys, int64_t E, const long long*
         if (base + j < E) mask[base + j] = (uint8_t)((mbits >> (8 * j)) & 1);
     }
   }
-  if (n_sel_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kChunkThreads - 1)
-    *n_sel_out = g_before + (e_before < avail ? e_before : avail);
+  __syncthreads();
+  const long long e_end = be + tot_e;
+  const int n_out = tot_g + (int)((e_end < avail ? e_end : avail) - be_taken);
+  if (sel) {
+    for (int i = threadIdx.x; i < n_out; i += kChunkThreads)
+      if (pos_block0 + i < q_cap) sel[pos_block0 + i] = stage[i];
+  }
+  if (n_sel_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_sel_out = pos_block0 + n_out;
 }
 
 // ---------------------------------------------------------------------------------------

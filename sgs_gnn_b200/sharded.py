@@ -700,13 +700,13 @@ def allreduce_partial_grads(params, comm):
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
                       for p in ps] + [has])
     comm.all_reduce(flat)
-    seen = flat[-len(ps):].cpu()
+    # the bitmap is only read (one small D2H) when some local gradient is None; the usual learned-wins step has none
+    seen = flat[-len(ps):].cpu() if any(p.grad is None for p in ps) else None
     off = 0
     for i, p in enumerate(ps):
         k = p.numel()
-        if float(seen[i]) > 0.0:
-            if p.grad is None:
-                p.grad = flat[off:off + k].view_as(p).clone()
-            else:
-                p.grad.copy_(flat[off:off + k].view_as(p))
+        if p.grad is not None:
+            p.grad.copy_(flat[off:off + k].view_as(p))
+        elif float(seen[i]) > 0.0:
+            p.grad = flat[off:off + k].view_as(p).clone()
         off += k
