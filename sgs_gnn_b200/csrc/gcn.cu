@@ -2,6 +2,7 @@
 // bias gradient and the edge-weight gradient (SDDMM + per-node sums).
 // All segment reductions are atomic-free: one warp owns one CSR row.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -330,6 +331,63 @@ struct SpmmRowH {
       }
     }
   }
+  // K == 1 (D <= 256): software-pipelined form.  A ring of RING row loads stays in flight -- the load of edge
+  // j + RING is issued before the FMAs of edge j, so there is no drain bubble between 8-edge batches -- and the
+  // (nbr, what) pairs of the NEXT 32-edge group are fetched while this group is processed.  (The plain form above pays
+  // one exposed L2 latency per batch and per group: ~20 per average row of ~100 edges.)
+  __device__ __forceinline__ void gather_pipelined(const int32_t* __restrict__ nbr, const float* __restrict__ what,
+                                                   const __half* __restrict__ h, int D, int lane, int beg, int end,
+                                                   int first, int nstep) {
+    static_assert(K == 1, "pipelined gather: one 8-column chunk per lane");
+    constexpr int RING = 8;
+    const int c = lane * 8;
+    const bool act = c < D;
+    int base = beg + 32 * first;
+    if (base >= end) return;
+    int nn = 0;
+    float nw = 0.f;
+    if (base + lane < end) {
+      nn = nbr[base + lane];
+      nw = what[base + lane];
+    }
+    while (base < end) {
+      const int my_n = nn;
+      const float my_w = nw;
+      const int nbase = base + 32 * nstep;
+      nn = 0;
+      nw = 0.f;
+      if (nbase + lane < end) {   // in flight during this group
+        nn = nbr[nbase + lane];
+        nw = what[nbase + lane];
+      }
+      const int cnt = min(32, end - base);
+      uint4 ring[RING];
+#pragma unroll
+      for (int j = 0; j < RING; ++j) {
+        const int n = __shfl_sync(0xffffffffu, my_n, j);
+        ring[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (j < cnt && act) ring[j] = *reinterpret_cast<const uint4*>(h + (int64_t)n * D + c);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += RING) {
+        if (jj < cnt) {   // warp-uniform
+#pragma unroll
+          for (int r = 0; r < RING; ++r) {
+            const int j = jj + r;
+            const uint4 v = ring[r];
+            const float wv = __shfl_sync(0xffffffffu, my_w, j);                  // 0 for j >= cnt
+            const int n2 = __shfl_sync(0xffffffffu, my_n, (j + RING) & 31);
+            if (j + RING < cnt && act) ring[r] = *reinterpret_cast<const uint4*>(h + (int64_t)n2 * D + c);
+            float x[8];
+            h8_to_float(v, x);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[0][t] = fmaf(wv, x[t], acc[0][t]);
+          }
+        }
+      }
+      base = nbase;
+    }
+  }
   __device__ __forceinline__ void finish(int64_t row, const float* __restrict__ dis, const float* __restrict__ loopw,
                                          const __half* __restrict__ h, int D, int lane, float inv_scale,
                                          const float* __restrict__ bias, float* __restrict__ out, int flags,
@@ -380,8 +438,8 @@ struct SpmmRowH {
   }
 };
 
-template <int K>
-__global__ void __launch_bounds__(kBlock)
+template <int K, bool PIPE>
+__global__ void __launch_bounds__(kBlock, PIPE ? 2 : 4)
 spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ what,
                 const float* __restrict__ dis, const float* __restrict__ loopw, const __half* __restrict__ h,
                 const float* __restrict__ tscale, int64_t N, int D, const float* __restrict__ bias,
@@ -394,11 +452,15 @@ spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   const float inv_scale = tscale[1];
   const int n_heavy = order ? order[N] : 0;
   SpmmRowH<K> r;
+  auto do_gather = [&](int beg, int end, int first, int nstep) {
+    if constexpr (K == 1 && PIPE) r.gather_pipelined(nbr, what, h, D, lane, beg, end, first, nstep);
+    else r.gather(nbr, what, h, D, lane, beg, end, first, nstep);
+  };
   for (int hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
     const int64_t row = order[hidx];
     if (row < pe.row_lo || row >= pe.row_hi) continue;   // block-uniform
     r.clear();
-    r.gather(nbr, what, h, D, lane, rowptr[row], rowptr[row + 1], warp, kWarpsPerBlock);
+    do_gather(rowptr[row], rowptr[row + 1], warp, kWarpsPerBlock);
     if (warp > 0) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -416,14 +478,33 @@ spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     }
     __syncthreads();
   }
-  int64_t idx = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  // one warp per row, rows dealt heaviest-first.  The row id and the extent of the NEXT row are fetched while the
+  // current row is gathered (two dependent loads -- order[], rowptr[] -- off the critical path of every row).
   const int64_t step = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t idx = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  auto row_of = [&](int64_t i) -> int64_t { return i < N ? (order ? (int64_t)order[i] : i) : -1; };
+  int64_t row = row_of(idx), row1 = row_of(idx + step);
+  int beg = 0, end = 0;
+  if (row >= 0) {
+    beg = rowptr[row];
+    end = rowptr[row + 1];
+  }
   for (; idx < N; idx += step) {
-    const int64_t row = order ? order[idx] : idx;
-    if (row < pe.row_lo || row >= pe.row_hi) continue;
-    r.clear();
-    r.gather(nbr, what, h, D, lane, rowptr[row], rowptr[row + 1], 0, 1);
-    r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed, pe);
+    const int64_t row2 = row_of(idx + 2 * step);
+    int beg1 = 0, end1 = 0;
+    if (row1 >= 0) {
+      beg1 = rowptr[row1];
+      end1 = rowptr[row1 + 1];
+    }
+    if (row >= pe.row_lo && row < pe.row_hi) {
+      r.clear();
+      do_gather(beg, end, 0, 1);
+      r.finish(row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed, pe);
+    }
+    row = row1;
+    row1 = row2;
+    beg = beg1;
+    end = end1;
   }
 }
 
@@ -756,12 +837,21 @@ static int32_t spmm_impl(const int32_t* rowptr, const int32_t* nbr, const float*
   if ((flags & SGS_SPMM_DROPOUT) && p_drop == 0.f) flags &= ~SGS_SPMM_DROPOUT;
   if (h16) {
     const __half* hh = reinterpret_cast<const __half*>(h16);
-    if (D <= 256)
-      spmm_h16_kernel<1><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias,
-                                                         out, flags, p_drop, seed, order, pe);
+    // SGS_SPMM_PIPE=0 selects the plain (r02a) gather loop for A/B measurements
+    static int pipe = -1;
+    if (pipe < 0) {
+      const char* e = getenv("SGS_SPMM_PIPE");
+      pipe = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (D <= 256 && pipe)
+      spmm_h16_kernel<1, true><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D,
+                                                               bias, out, flags, p_drop, seed, order, pe);
+    else if (D <= 256)
+      spmm_h16_kernel<1, false><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D,
+                                                                bias, out, flags, p_drop, seed, order, pe);
     else
-      spmm_h16_kernel<2><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias,
-                                                         out, flags, p_drop, seed, order, pe);
+      spmm_h16_kernel<2, false><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D,
+                                                                bias, out, flags, p_drop, seed, order, pe);
     SGS_LAUNCH_CHECK();
     return SGS_OK;
   }
