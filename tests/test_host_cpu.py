@@ -1,0 +1,48 @@
+"""CPU: host-side logic added in round 2 that needs no GPU -- the prefetching loader's pass-through / ordering,
+compact host batches, the deferred validity checks of the training loop."""
+import pytest
+import torch
+
+from sgs_gnn_b200 import _train_core, loader, synth
+
+
+def test_prefetch_passes_cpu_and_resident_batches_through_in_order():
+    bs = [synth.make_graph(None, seed=s, n=40, e=160, f=4, c=2) for s in range(3)]
+    out = list(loader.prefetch(bs, "cpu"))
+    assert len(out) == 3 and all(a is b for a, b in zip(out, bs))
+    assert list(loader.prefetch([], "cpu")) == []
+    # a generator loader is consumed lazily, one element ahead
+    seen = []
+
+    def gen():
+        for b in bs:
+            seen.append(1)
+            yield b
+    it = loader.prefetch(gen(), "cpu")
+    first = next(it)
+    assert first is bs[0] and len(seen) == 2
+    assert [b is c for b, c in zip(list(it), bs[1:])] == [True, True]
+
+
+def test_compact_batch_keeps_everything_but_the_index_dtype():
+    b = synth.make_graph(None, seed=1, n=50, e=200, f=4, c=2)
+    c = b.compact()
+    assert c.edge_index.dtype == torch.int32 and torch.equal(c.edge_index.long(), b.edge_index)
+    assert c.x is b.x and c.prob is b.prob and c.num_classes == b.num_classes
+    assert c.nbytes() == b.nbytes() - b.edge_index.numel() * 4
+    assert c.compact().edge_index.dtype == torch.int32
+
+
+def test_deferred_checks_raise_like_the_reference():
+    loss = torch.tensor(1.25)
+    ok = torch.tensor([0, 0, 0, 0, 0, 0, 0, 7], dtype=torch.int64)
+    assert _train_core._read_loss_and_checks(loss, [], 7) == 1.25
+    assert _train_core._read_loss_and_checks(loss, [("sampler", ok), ("oob", torch.zeros(1, dtype=torch.int32))], 7) == 1.25
+    bad = ok.clone()
+    bad[5] = 1
+    with pytest.raises(RuntimeError, match="inf"):
+        _train_core._read_loss_and_checks(loss, [("sampler", bad)], 7)
+    with pytest.raises(RuntimeError, match="expected 7"):
+        _train_core._read_loss_and_checks(loss, [("sampler", torch.tensor([0, 0, 0, 0, 0, 0, 0, 6]))], 7)
+    with pytest.raises(RuntimeError, match="outside"):
+        _train_core._read_loss_and_checks(loss, [("oob", torch.ones(1, dtype=torch.int32))], 7)
