@@ -504,21 +504,34 @@ topq_write_kernel(const uint32_t* __restrict__ keys, int64_t E, const long long*
   const long long bg = blk_gt[blockIdx.x], be = blk_eq[blockIdx.x];
   const long long be_taken = be < avail ? be : avail;        // ties taken before this chunk
   const long long pos_block0 = bg + be_taken;                // output position of the chunk's first selected id
-  long long g_before = bg + wg[wid] + (ig - gt);
-  long long e_before = be + we[wid] + (ie - eq);
   uint64_t mbits = 0;
+  if (tot_e == 0) {
+    // no threshold tie in this chunk (ties are a handful per 10^8 keys): block-local positions in 32-bit arithmetic
+    int loc = wg[wid] + (ig - gt);
+    const int32_t id0 = (int32_t)base;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const bool in = base + j < E;
-    const bool is_gt = in && (k[j] > tau);
-    const bool is_eq = in && (k[j] == tau);
-    if (is_gt || (is_eq && e_before < avail)) {
-      const long long pos = g_before + (e_before < avail ? e_before : avail);
-      stage[(int)(pos - pos_block0)] = (int32_t)(base + j);
-      mbits |= (uint64_t)1 << (8 * j);
+    for (int j = 0; j < 8; ++j) {
+      if (base + j < E && k[j] > tau) {
+        stage[loc++] = id0 + j;
+        mbits |= (uint64_t)1 << (8 * j);
+      }
     }
-    g_before += is_gt;
-    e_before += is_eq;
+  } else {
+    long long g_before = bg + wg[wid] + (ig - gt);
+    long long e_before = be + we[wid] + (ie - eq);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = base + j < E;
+      const bool is_gt = in && (k[j] > tau);
+      const bool is_eq = in && (k[j] == tau);
+      if (is_gt || (is_eq && e_before < avail)) {
+        const long long pos = g_before + (e_before < avail ? e_before : avail);
+        stage[(int)(pos - pos_block0)] = (int32_t)(base + j);
+        mbits |= (uint64_t)1 << (8 * j);
+      }
+      g_before += is_gt;
+      e_before += is_eq;
+    }
   }
   if (mask) {
     if (base + 8 <= E && ((uintptr_t)(mask + base) & 7) == 0) {
