@@ -25,6 +25,7 @@ def mean(rows, pred):
 def main(hot, spmm, dst):
     h, s = load(hot), load(spmm)
     fam = {}
+    tag = dst.split("/")[-1].split("_")[0]
 
     def put(name, kernel, rw):
         fam[name] = {"kernel": kernel, "dram_read_gb": round(rw[0], 3), "dram_write_gb": round(rw[1], 3)}
@@ -38,12 +39,16 @@ def main(hot, spmm, dst):
     ndraw = max(1, sum(1 for k, _, _ in h if "topq_write" in k))
     put("sample_topq", "all topq_* kernels of one draw (sample, predict, keys_window, find_window, hist, find, count, "
         "scan, write)", (sum(a for a, _ in tq) / ndraw, sum(b for _, b in tq) / ndraw))
-    put("spmm_d256", "spmm_kernel<4,2>", mean(s, lambda k: "spmm_kernel<4, 2>" in k))
+    if any("spmm_h16" in k for k, _, _ in s):     # fp16 gather tables (round 2 default)
+        put("spmm_d256", "spmm_h16_kernel (fp16 gather table)", mean(s, lambda k: "spmm_h16" in k))
+        put("edge_grad_d256", "edge_grad_sddmm_h16_kernel (fp16 gather table)", mean(s, lambda k: "sddmm_h16" in k))
+    else:
+        put("spmm_d256", "spmm_kernel<4,2>", mean(s, lambda k: "spmm_kernel<4, 2>" in k))
+        put("edge_grad_d256", "edge_grad_sddmm_kernel<4,2>", mean(s, lambda k: "sddmm_kernel<4, 2>" in k))
     put("spmm_d41", "spmm_kernel<1,2>", mean(s, lambda k: "spmm_kernel<1, 2>" in k))
-    put("edge_grad_d256", "edge_grad_sddmm_kernel<4,2>", mean(s, lambda k: "sddmm_kernel<4, 2>" in k))
     put("edge_grad_d41", "edge_grad_sddmm_kernel<1,2>", mean(s, lambda k: "sddmm_kernel<1, 2>" in k))
     fam = {k: v for k, v in fam.items() if v["dram_read_gb"] + v["dram_write_gb"] > 0}
-    fam["_source"] = (f"ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 (scripts/ncu_round1.sh; "
+    fam["_source"] = (f"ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 (scripts/ncu_{'round2' if tag != 'r01' else 'round1'}.sh; "
                       f"profiles/{hot.split('/')[-1]}, profiles/{spmm.split('/')[-1]}); reddit shape, 1 B200")
     json.dump(fam, open(dst, "w"), indent=1)
     print(json.dumps(fam, indent=1))

@@ -10,8 +10,9 @@ figure is also written to gpurun_out/parity_benched.json (committed copy: profil
     reference's; later epochs within P_ATOL (the weights themselves have drifted by then, see PARAM_TOL),
   * sampled-set overlap with the reference's mask >= OVERLAP_MIN, every epoch (same injected noise),
   * final parameters after 6 Adam epochs within PARAM_TOL * (1 + max|ref|).  Adam normalises every element's step
-    to ~lr, so an element whose gradient is rounding noise can move by lr per epoch in either direction whatever the
-    precision: the bound is 2 * lr * epochs = 1.2e-2 (measured 0.8e-2 .. 1.1e-2 in every mode, tf32 included).
+    to ~lr, so an element whose gradient is rounding noise can move by lr per optimiser step in either direction
+    whatever the precision; the scorer's gcn* weights sit in BOTH optimisers (main.py:100,122) and are stepped twice
+    per learned epoch.  Bound: 2.4e-2 = 2 * lr * 12 steps (measured 0.9e-2 .. 1.1e-2 in every mode, tf32 included).
 """
 import json
 import os
@@ -26,11 +27,12 @@ from conftest import ROOT, FixtureBatch, load_golden, t
 
 pytestmark = pytest.mark.gpu
 
-# measured on B200 (round 2; loss <= 3.5e-4 / 1.3e-3 bf16, p0 6e-5 / 2e-4 bf16, overlap >= 0.99925) with head-room
+# measured on B200 (profiles/r02_parity_benched.json: loss <= 6.5e-4, p0 <= 3e-5 / 2e-4 bf16, overlap >= 0.999,
+# parameters <= 1.1e-2) with head-room for run-to-run noise (float atomics in the scorer backward / loss kernels)
 BOUNDS = {
-    "fp16": dict(LOSS_RTOL=1e-3, P0_ATOL=2e-4, P_ATOL=1e-2, OVERLAP_MIN=0.999, PARAM_TOL=1.2e-2),
-    "bf16": dict(LOSS_RTOL=4e-3, P0_ATOL=6e-4, P_ATOL=2e-2, OVERLAP_MIN=0.998, PARAM_TOL=1.2e-2),
-    "tf32": dict(LOSS_RTOL=1e-3, P0_ATOL=1e-4, P_ATOL=1e-2, OVERLAP_MIN=0.999, PARAM_TOL=1.2e-2),
+    "fp16": dict(LOSS_RTOL=2e-3, P0_ATOL=1e-4, P_ATOL=2e-2, OVERLAP_MIN=0.997, PARAM_TOL=2.4e-2),
+    "bf16": dict(LOSS_RTOL=4e-3, P0_ATOL=6e-4, P_ATOL=2e-2, OVERLAP_MIN=0.997, PARAM_TOL=2.4e-2),
+    "tf32": dict(LOSS_RTOL=2e-3, P0_ATOL=1e-4, P_ATOL=2e-2, OVERLAP_MIN=0.997, PARAM_TOL=2.4e-2),
 }
 
 
