@@ -70,6 +70,12 @@ int32_t sgs_edge_index_check32(const int32_t* src, const int32_t* dst, int64_t M
 int32_t sgs_edge_gather32(const int32_t* src, const int32_t* dst, const int32_t* ids, int64_t q, int64_t* out,
                           int32_t* src_out, int32_t* dst_out, sgs_stream_t stream);
 
+/* The degree prior `data.prob` of datasets.py:141-156 BEFORE its softmax (finish with sgs_softmax_f32):
+ * out[e] = len^-1/2 / (colcount[src_e] + rowcount[dst_e] + 1e-10), every fp32 operation as the reference performs it
+ * (1/(1/count) included).  counts: int32 [2N] scratch (row counts | column counts). */
+int32_t sgs_degree_scores(const int32_t* src, const int32_t* dst, int64_t M, int64_t N, int32_t* counts, float* out,
+                          sgs_stream_t stream);
+
 size_t sgs_csr_workspace_bytes(int64_t M, int64_t N);
 /* Stable counting sort of the M edges by key (dst for the forward CSR, src for the backward
  * one): rowptr[N+1], perm[M] = edge ids in key order, nbr[M] = other[perm]; optional order[N+1]:

@@ -29,6 +29,7 @@ SIGNATURES = {
     "sgs_edge_index_gather": (I32, [P, I64, P, I64, P, P, P, P]),
     "sgs_edge_index_check32": (I32, [P, P, I64, I64, P, P]),
     "sgs_edge_gather32": (I32, [P, P, P, I64, P, P, P, P]),
+    "sgs_degree_scores": (I32, [P, P, I64, I64, P, P, P]),
     "sgs_csr_workspace_bytes": (SZ, [I64, I64]),
     "sgs_csr_build": (I32, [P, P, I64, I64, P, P, P, P, P, SZ, P]),
     "sgs_csr_build_sorted": (I32, [P, P, I64, I64, P, P, P, P, P, SZ, P]),

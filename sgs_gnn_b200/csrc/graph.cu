@@ -1,6 +1,8 @@
 // Graph preparation: int64 COO -> int32, column gathers, CSR (by dst / by src) construction.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <math.h>
+
 #include "common.cuh"
 
 namespace sgs {
@@ -65,6 +67,30 @@ __global__ void edge_gather32_kernel(const int32_t* __restrict__ src, const int3
     }
     if (so) so[i] = s;
     if (dout) dout[i] = d;
+  }
+}
+
+// Degree prior of datasets.py:141-156 (before its softmax): counts by atomics, then, op for op in fp32 as the
+// reference evaluates it,  score_e = E^-1/2 / ( 1/(1/colcount[row_e]) + 1/(1/rowcount[col_e]) + 1e-10 ).
+__global__ void degree_count_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int64_t M,
+                                    int32_t* __restrict__ rowcount, int32_t* __restrict__ colcount) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < M; i += stride) {
+    atomicAdd(rowcount + src[i], 1);
+    atomicAdd(colcount + dst[i], 1);
+  }
+}
+__global__ void degree_score_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int64_t M,
+                                    const int32_t* __restrict__ rowcount, const int32_t* __restrict__ colcount,
+                                    float scale, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < M; i += stride) {
+    const float deg_in = __fdiv_rn(1.0f, (float)colcount[src[i]]);    // deg_in[row]
+    const float deg_out = __fdiv_rn(1.0f, (float)rowcount[dst[i]]);   // deg_out[col]
+    const float p = __fadd_rn(__fdiv_rn(1.0f, deg_in), __fdiv_rn(1.0f, deg_out));
+    out[i] = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(p, 1e-10f)), scale);
   }
 }
 
@@ -191,6 +217,22 @@ int32_t sgs_edge_gather32(const int32_t* src, const int32_t* dst, const int32_t*
   if (q == 0) return SGS_OK;
   SGS_CHECK_ARG(src && dst && ids, "null pointer");
   edge_gather32_kernel<<<grid_for(q, 256), 256, 0, as_stream(stream)>>>(src, dst, ids, q, out, src_out, dst_out);
+  SGS_LAUNCH_CHECK();
+  return SGS_OK;
+}
+
+int32_t sgs_degree_scores(const int32_t* src, const int32_t* dst, int64_t M, int64_t N, int32_t* counts, float* out,
+                          sgs_stream_t stream) {
+  SGS_CHECK_ARG(M >= 0 && N > 0, "bad sizes");
+  if (M == 0) return SGS_OK;
+  SGS_CHECK_ARG(src && dst && counts && out, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  SGS_CUDA(cudaMemsetAsync(counts, 0, (size_t)2 * N * sizeof(int32_t), st));
+  degree_count_kernel<<<grid_for(M, 256), 256, 0, st>>>(src, dst, M, counts, counts + N);
+  SGS_LAUNCH_CHECK();
+  // len(prob) ** -0.5 is evaluated by Python in double and meets the fp32 tensor as an fp32 scalar
+  const float scale = (float)pow((double)M, -0.5);
+  degree_score_kernel<<<grid_for(M, 256), 256, 0, st>>>(src, dst, M, counts, counts + N, scale, out);
   SGS_LAUNCH_CHECK();
   return SGS_OK;
 }

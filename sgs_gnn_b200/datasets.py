@@ -6,21 +6,26 @@ Dataset download / METIS clustering (datasets.py, main.py:41-67) are outside the
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 
 def degree_prior(edge_index, num_nodes):
-    """softmax_e( E^-1/2 / (colcount[row_e] + rowcount[col_e] + 1e-10) ), op order as the reference.
-    `edge_index` must be sorted by (row, col) as PyG datasets are (adj.coo() returns that order)."""
-    row, col = edge_index[0], edge_index[1]
-    e = row.numel()
-    colcount = torch.bincount(col, minlength=num_nodes)
-    rowcount = torch.bincount(row, minlength=num_nodes)
-    deg_in = 1.0 / colcount
-    deg_out = 1.0 / rowcount
-    prob = (1.0 / deg_in[row]) + (1.0 / deg_out[col])
-    prob = 1.0 / (prob + 1e-10)
-    return F.softmax(prob * e ** -0.5, dim=0)
+    """softmax_e( E^-1/2 / (colcount[row_e] + rowcount[col_e] + 1e-10) ), every fp32 operation as the reference
+    performs it (datasets.py:147-155).  `edge_index` must be sorted by (row, col) as PyG datasets are (adj.coo()
+    returns that order).  Computed by libsgs_b200 kernels (sgs_degree_scores + sgs_softmax_f32); a host tensor -- the
+    reference prepares its data on the CPU -- is uploaded, processed on the device and the result copied back.  There
+    is no CPU implementation: without a GPU this raises like every other op of the package."""
+    from . import ops
+    if not edge_index.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("add_degree runs on the GPU (sgs_gnn_b200 has no CPU fallback)")
+        return degree_prior(edge_index.cuda(), num_nodes).to(edge_index.device)
+    g = ops.graph_of(edge_index, num_nodes)
+    e = g.num_edges
+    counts = torch.empty(2 * num_nodes, dtype=torch.int32, device=edge_index.device)
+    scores = torch.empty(e, dtype=torch.float32, device=edge_index.device)
+    ops.check(ops.lib().sgs_degree_scores(ops._p(g.src), ops._p(g.dst), e, int(num_nodes), ops._p(counts),
+                                          ops._p(scores), ops._stream()), "sgs_degree_scores")
+    return ops.softmax_f32(scores)
 
 
 def add_degree(data):

@@ -240,6 +240,32 @@ def golden_step(pipeline, tag, n, e, f, c, h, epochs, seed, record=False):
         **{"sd0." + k: v for k, v in sd0.items()}, **{"sd1." + k: v for k, v in sd1.items()})
 
 
+def golden_baseline_modes():
+    """training_hybrid.train in the baseline modes `full` and `edge` (training_hybrid.py:149-180) with `optimizer`
+    = Adam(lr 1e-3, weight_decay 5e-4) over all parameters (main.py:123): 6-epoch trajectories.  `edge` draws
+    torch.multinomial(softmax(prob), q) once per epoch; the Exp(1) tensors it drew are recorded."""
+    n, e, f, c, h, epochs = 300, 2400, 20, 4, 32, 6
+    for mode, seed in (("full", 91), ("edge", 93)):
+        b = synth.make_graph(None, seed=seed, n=n, e=e, f=f, c=c, homophily=0.7)
+        q = int(e * 0.2)
+        model, opt_gnn, opt_edge, opt_all = build_ref_model(f, h, c, 0.0, seed + 1)
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        args = make_args(mode=mode)
+        crit = nn.CrossEntropyLoss()
+        losses, noises = [], []
+        for ep in range(epochs):
+            torch.manual_seed(2000 + ep)
+            noises.append(ox.exponential_noise(e))
+            torch.manual_seed(2000 + ep)
+            loss, _, n_cond, n_tot = ref.training_hybrid.train(args, ep, epochs, model, opt_gnn, opt_edge, opt_all, crit,
+                                                               [b], q=q, alternate_frequency=0)
+            losses.append(loss)
+        print(mode, "losses", [round(x, 5) for x in losses])
+        npz(f"step_mode_{mode}.npz", x=b.x, y=b.y, edge_index=b.edge_index, train_mask=b.train_mask, prob=b.prob, q=q,
+            hidden=h, noises=torch.stack(noises), losses=np.array(losses),
+            **{"sd0." + k: v for k, v in sd0.items()}, **{"sd1." + k: v for k, v in model.state_dict().items()})
+
+
 def golden_eval():
     """evaluate.evaluate / evaluate.ensemble_evaluate (learned mode) on a model in eval mode; the Exp(1) noise
     torch.multinomial draws for each ensemble member is re-generated from the same seed and stored."""
@@ -272,7 +298,7 @@ def golden_eval():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     which = sys.argv[1:] or ["sampler", "forward", "hybrid", "st", "two_pass", "eval", "sage", "mlp", "hybrid_h256",
-                               "st_h256"]
+                               "st_h256", "modes"]
     if "mlp" in which:
         golden_mlp()
     if "sage" in which:
@@ -291,5 +317,7 @@ if __name__ == "__main__":
         golden_step("hybrid", "hybrid_h256", 1200, 20000, 48, 5, 256, 6, 71, record=True)
     if "st_h256" in which:
         golden_step("straight_through", "st_h256", 1200, 20000, 48, 5, 256, 6, 81, record=True)
+    if "modes" in which:
+        golden_baseline_modes()
     if "eval" in which:
         golden_eval()

@@ -222,3 +222,18 @@ def test_fp16_gather_tables_match_fp32_path(dev):
     assert rel(res["fp16"][1], res["fp32"][1]) < 1e-3
     for i in range(2, 6):
         assert rel(res["fp16"][i], res["fp32"][i]) < 2e-3, i
+
+
+def test_degree_prior_kernel_matches_reference_formula(dev):
+    """datasets.add_degree (datasets.py:141-156) on the device -- sgs_degree_scores + sgs_softmax_f32 --
+    against the oracle's restatement of the reference formula."""
+    from types import SimpleNamespace
+    from oracle import extended as ox
+    from sgs_gnn_b200 import datasets, synth
+    b = synth.make_graph("arxiv-year", seed=4, scale=0.05)
+    want = ox.degree_prior(b.edge_index, b.num_nodes)
+    data = SimpleNamespace(x=b.x.to(dev), edge_index=b.edge_index.to(dev), num_nodes=b.num_nodes)
+    datasets.add_degree(data)
+    got = data.prob.cpu()
+    assert got.shape == want.shape and abs(float(got.sum()) - 1.0) < 1e-4
+    assert float(((got - want).abs() / want).max()) < 1e-5

@@ -155,3 +155,37 @@ def test_prefetched_int32_host_batches_match_resident_training(dev):
     assert abs(res[0][0][0] - res[1][0][0]) < 1e-3 * max(1.0, abs(res[0][0][0]))
     for pa, pb in zip(res[0][1], res[1][1]):
         assert float((pa - pb).abs().max()) < 5e-3 * (1.0 + float(pa.abs().max()))
+
+
+@pytest.mark.parametrize("mode", ["full", "edge"])
+def test_baseline_modes_match_reference_training(dev, mode, monkeypatch):
+    """the `full` / `edge` baseline modes of training_hybrid.train (:149-180) with the `optimizer` of
+    main.py:123 (Adam, weight decay 5e-4, all parameters): 6-epoch golden trajectories of the reference
+    (tests/golden/step_mode_*.npz; `edge` with the Exp(1) tensors torch.multinomial drew injected)."""
+    from sgs_gnn_b200 import _train_core, sampling, training
+    from sgs_gnn_b200.model import GNNModel
+    z = load_golden(f"step_mode_{mode}.npz")
+    b = FixtureBatch(z, dev)
+    f, c, h, q = b.x.size(1), int(b.y.max()) + 1, int(z["hidden"]), int(z["q"])
+    model = GNNModel(f, h, c, 0.0, "GCN")
+    model.load_state_dict({k[4:]: t(v) for k, v in z.items() if k.startswith("sd0.")})
+    model = model.to(dev)
+    opt_gnn = torch.optim.Adam([p for n, p in model.named_parameters() if "gcn" in n], lr=1e-3)
+    opt_edge = torch.optim.Adam([p for n, p in model.named_parameters() if "edge_prob_mlp" in n], lr=1e-3)
+    opt_all = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    scores = torch.softmax(t(z["prob"]), -1).to(dev)
+    monkeypatch.setattr(_train_core, "_softmax_prob", lambda prob: scores)
+    args = make_args(dev, mode=mode)
+    noises = t(z["noises"], dev)
+    for ep in range(noises.size(0)):
+        sampling.clear_injected()
+        sampling.inject_noise([noises[ep].contiguous()])
+        loss, _, n_cond, n_tot = training.train(args, ep, noises.size(0), model, opt_gnn, opt_edge, opt_all,
+                                                nn.CrossEntropyLoss(), [b], q=q, alternate_frequency=0)
+        assert (n_cond, n_tot) == (0, 1)
+        assert abs(loss - float(z["losses"][ep])) < 2e-4 * max(1.0, abs(float(z["losses"][ep]))), (ep, loss)
+    sd1 = model.state_dict()
+    for k, v in z.items():
+        if k.startswith("sd1."):
+            got, want = sd1[k[4:]].cpu(), t(v)
+            assert float((got - want).abs().max()) < 2e-4 * (1.0 + float(want.abs().max())), k

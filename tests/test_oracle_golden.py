@@ -113,11 +113,16 @@ def test_add_degree_dropin_matches_oracle():
     from types import SimpleNamespace
     from sgs_gnn_b200 import datasets, synth
     b = synth.make_graph("amazon-ratings", seed=5, scale=0.2)
-    d = SimpleNamespace(edge_index=b.edge_index, x=b.x, num_nodes=b.num_nodes)
-    datasets.add_degree(d)
-    assert torch.equal(d.prob, ox.degree_prior(b.edge_index, b.num_nodes))
-    d.edge_index = b.edge_index.flip(1)
     import pytest
+    d = SimpleNamespace(edge_index=b.edge_index, x=b.x, num_nodes=b.num_nodes)
+    if torch.cuda.is_available():      # host data: uploaded, computed by the kernels, copied back
+        datasets.add_degree(d)
+        want = ox.degree_prior(b.edge_index, b.num_nodes)
+        assert d.prob.device.type == "cpu" and float(((d.prob - want).abs() / want).max()) < 1e-5
+    else:                              # no GPU: fails loudly, there is no CPU implementation
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            datasets.add_degree(d)
+    d.edge_index = b.edge_index.flip(1)
     with pytest.raises(RuntimeError, match="sorted"):
         datasets.add_degree(d)
 
