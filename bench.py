@@ -329,8 +329,19 @@ def run_gpu_arm(a):
     ops.set_precision(gemm=a.gemm_precision, scorer=a.precision, gather=a.gather_precision)
     _lib.lib()
 
-    shard = world > 1 and a.parallel == "shard"
-    if shard:
+    shard = world > 1 and a.parallel == "shard" and not a.clusters
+    clusters = None
+    if a.clusters:
+        # the reference's own regime (main.py:41-67): the graph cut into `clusters` mini-batches of ~threshold edges,
+        # one learned step per cluster, q = int(threshold * perc) per cluster; a "step" of the bench is then one
+        # train() call over all clusters -- an epoch in the reference's sense (11.77 s on its GPU)
+        if world > 1:
+            raise SystemExit("--clusters runs on one GPU")
+        clusters = synth.make_clusters(a.workload, a.clusters, seed=42, device=dev)
+        batch = clusters[0]
+        n, f, c = sum(b.num_nodes for b in clusters), batch.x.size(1), batch.num_classes
+        e = sum(b.num_edges for b in clusters)
+    elif shard:
         # ONE graph, edges sharded by destination-node range over the ranks (strong scaling)
         from sgs_gnn_b200 import sharded
         full = synth.make_graph(a.workload, seed=42, device=dev, scale=a.scale)
@@ -343,10 +354,14 @@ def run_gpu_arm(a):
         batch = synth.make_graph(a.workload, seed=42 + rank, device=dev, scale=a.scale)
         n, e, f, c = batch.num_nodes, batch.num_edges, batch.x.size(1), batch.num_classes
     q = int(e * a.sample_perc)
+    q_call = q                        # the q handed to train(): per batch
+    if clusters is not None:
+        q_call = int(clusters[0].num_edges * a.sample_perc)
+        q = q_call * len(clusters)
     units = 1 if shard else world     # graphs processed per step over all ranks
     model, og, oe, oa = build_model(f, c, dev, a.drop_rate)
     args = make_args(dev, a.drop_rate)
-    chk = selection_checksum(model, batch, q, shard) if (shard or world == 1) else None
+    chk = selection_checksum(model, batch, q_call, shard) if (shard or world == 1) else None
     args.data_parallel = world > 1 and not shard   # independent graph batches per rank + weight-gradient all-reduce
     # The reference's conditional gate (training_hybrid.py:92-101) skips the scorer backward whenever the random
     # baseline wins, which makes a step ~2x cheaper.  By default the bench computes the gate (both forwards, the
@@ -367,10 +382,10 @@ def run_gpu_arm(a):
         train_mod = training_hybrid
 
     def epoch(loader, ep):
-        return train_mod.train(args, ep, 1000, model, og, oe, oa, crit, loader, q=q, alternate_frequency=0)
+        return train_mod.train(args, ep, 1000, model, og, oe, oa, crit, loader, q=q_call, alternate_frequency=0)
 
     # ---- resident arm ----
-    loader = [batch]
+    loader = [batch] if clusters is None else clusters
     # warm-up: one step with the gate off forces the learned branch, so every workspace the step can need is
     # allocated (and cached by the allocator) before timing; then W regular steps
     args.conditional = False
@@ -469,7 +484,7 @@ def run_gpu_arm(a):
     # call over a loader of K host batches (an epoch over K cluster batches, as the reference's loop is shaped): the
     # loop's prefetcher (sgs_gnn_b200/loader.py) uploads batch k+1 on a copy stream while step k computes.
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and clusters is None:
         host = batch.to("cpu")
         if a.host_index == "int32":
             host = host.compact()
@@ -525,8 +540,8 @@ def run_gpu_arm(a):
                 "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
                 "peak_source": f"{pk['src']} bf16 sustained", "launches_timed": k1_n,
                 "avg_launch_ms": k1_ms / max(k1_n, 1),
-                "hbm_view": {"algorithmic_bytes": e_k1 * 1032 + n * 1028,
-                             "achieved_gbs": (e_k1 * 1032 + n * 1028) / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0,
+                "hbm_view": {"algorithmic_bytes": e_k1 * 1032 + batch.x.size(0) * 1028,
+                             "achieved_gbs": (e_k1 * 1032 + batch.x.size(0) * 1028) / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0,
                              "peak_gbs": pk["hbm"]}}
     shares = {k: round(v[0] / ms, 4) for k, v in sorted(ktot.items(), key=lambda kv: -kv[1][0])}
     # measured DRAM bytes per launch (ncu --set full capture of this very command, newest round first); a CONSTANT
@@ -544,20 +559,21 @@ def run_gpu_arm(a):
         roofline["traffic_source"] = traffic.get("_source")
 
     # every timed kernel family against the roofline that bounds it (SURVEY 8(d)-bis algorithmic work per launch)
-    q_loc = q // world if shard else q
-    nnz = q_loc + n
+    q_loc = q // world if shard else q_call      # per launch
+    n_b = batch.x.size(0)
+    nnz = q_loc + n_b
     n_train = int(batch.train_mask.sum())
     alg = {
         "edge_score_bwd": ("tensor", (q_loc if a.pipeline == "hybrid" else e_k1) * 787968.0),
-        "spmm_d256": ("hbm", nnz * (4 * 256 + 8) + n * (4 * 256 + 4)),
-        f"spmm_d{c}": ("hbm", nnz * (4 * c + 8) + n * (4 * c + 4)),
+        "spmm_d256": ("hbm", nnz * (4 * 256 + 8) + n_b * (4 * 256 + 4)),
+        f"spmm_d{c}": ("hbm", nnz * (4 * c + 8) + n_b * (4 * c + 4)),
         "edge_grad_d256": ("hbm", nnz * (2 * 4 * 256 + 12)),
         f"edge_grad_d{c}": ("hbm", nnz * (2 * 4 * c + 12)),
         "sample_topq": ("hbm", e_k1 * 20 + q_loc * 12),
         # K5: the fused forward sweep reads 2 logit rows + ids + p per sampled edge AND accumulates
         # the unscaled row gradients (2 rows), writes u1/u2; the backward is the two streaming passes left over
-        "loss_fwd": ("hbm", q_loc * (2 * 4 * c + 12 + 2 * 4 * c + 8) + n * (4 * c + 9)),
-        "loss_bwd": ("hbm", q_loc * 12 + n * (3 * 4 * c + 9)),
+        "loss_fwd": ("hbm", q_loc * (2 * 4 * c + 12 + 2 * 4 * c + 8) + n_b * (4 * c + 9)),
+        "loss_bwd": ("hbm", q_loc * 12 + n_b * (3 * 4 * c + 9)),
     }
     kernels = []
     for name, (bound, work) in alg.items():
@@ -592,7 +608,9 @@ def run_gpu_arm(a):
             # same fixed graph, so it carries the same label
             "scaling": "strong" if a.parallel == "shard" else "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32"}.get(a.precision, a.precision), "data": "synthetic",
-            "config": {"workload": f"{a.workload}-shape hybrid epoch, single full-graph batch" +
+            "config": {"workload": (f"{a.workload}-shape hybrid epoch, single full-graph batch" if clusters is None else
+                                    f"{a.workload}-shape epoch over {len(clusters)} virtual cluster batches "
+                                    f"({clusters[0].num_nodes} nodes, {clusters[0].num_edges} edges, q {q_call} each)") +
                                    ("" if a.scale == 1.0 else f" (scaled {a.scale:g}x)"),
                        "nodes": n, "edges": e, "features": f, "classes": c, "hidden": HIDDEN, "q": q,
                        "sample_perc": a.sample_perc, "drop_rate": a.drop_rate, "pipeline": a.pipeline,
@@ -644,6 +662,9 @@ def main():
                     help="--impl reference: host cores (the driver's arm) or stock torch-eager on this GPU")
     ap.add_argument("--host-index", default="int32", choices=["int32", "int64"],
                     help="e2e arm: dtype of edge_index in the pinned host batch (int64 = the reference's form)")
+    ap.add_argument("--clusters", type=int, default=0,
+                    help="cut the workload into this many independent cluster batches (the reference's METIS regime, "
+                         "main.py:41-67); a step is then one train() call over all of them")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

@@ -7,6 +7,7 @@ run --steps 5 --warmup 3 --pipeline straight_through --no-e2e                 # 
 run --steps 3 --warmup 3 --precision tf32 --no-e2e                            # tensor-core fp32-parity mode
 run --steps 5 --warmup 3 --workload ogbn-products                             # config 5 at N = 1
 run --steps 20 --warmup 5 --workload smallcora                                # config 0
+run --steps 3 --warmup 3 --clusters 230 --no-e2e                              # the reference's own regime (main.py:41-67): 230 cluster batches
 for w in amazon-ratings arxiv-year; do                                        # config 4: 10-50 % edge budget
   for sp in 0.1 0.2 0.3 0.4 0.5; do run --steps 20 --warmup 5 --workload $w --sample-perc $sp --no-e2e; done
 done

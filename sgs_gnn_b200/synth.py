@@ -187,3 +187,16 @@ def make_graph(shape="smallcora", seed=42, device="cpu", scale=1.0, undirected=N
     prob = degree_prior(ei, n)
     return Batch(x=x, y=y, edge_index=ei, train_mask=tm, val_mask=vm, test_mask=sm, prob=prob,
                  num_classes=c)
+
+
+def make_clusters(shape, parts, seed=42, device="cpu", edges_per_part=None):
+    """METIS-free "virtual clusters" (SURVEY 8f rank 3): `parts` independent graphs that together have the shape's
+    edge count, standing in for the reference's ClusterData / ClusterLoader mini-batches (main.py:41-67: graphs with
+    >= metis_threshold edges are cut into ceil(E / threshold) parts and inter-cluster edges dropped).  Every cluster
+    is a `Batch` of its own (local node ids, its own degree prior); its node count is the shape's share of nodes, but
+    never so small that edges_per_part distinct edges would not fit comfortably."""
+    n0, e0 = SHAPES[shape][:2]
+    e_p = int(edges_per_part if edges_per_part is not None else e0 // parts)
+    e_p -= e_p % 2
+    n_p = max(n0 // parts, int(8 * e_p ** 0.5) + 1)
+    return [make_graph(shape, seed=seed + 7 * k, device=device, n=n_p, e=e_p) for k in range(parts)]
