@@ -363,11 +363,14 @@ struct SpmmRowH {
       }
       const int cnt = min(32, end - base);
       uint4 ring[RING];
+      // (loads are never conditional on the edge count: a predicated refill compiles to "load into a temporary,
+      // then select", and the select waits for the load -- ncu r02a: long-scoreboard stalls on exactly those MOVs.
+      // Slots past the group's end re-load its last row -- an L1 hit -- and meet a zero weight.)
+      const int last = cnt - 1;
 #pragma unroll
       for (int j = 0; j < RING; ++j) {
-        const int n = __shfl_sync(0xffffffffu, my_n, j);
-        ring[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (j < cnt && act) ring[j] = *reinterpret_cast<const uint4*>(h + (int64_t)n * D + c);
+        const int n = __shfl_sync(0xffffffffu, my_n, min(j, last));
+        ring[j] = *reinterpret_cast<const uint4*>(h + (int64_t)n * D + (act ? c : 0));
       }
 #pragma unroll
       for (int jj = 0; jj < 32; jj += RING) {
@@ -377,8 +380,8 @@ struct SpmmRowH {
             const int j = jj + r;
             const uint4 v = ring[r];
             const float wv = __shfl_sync(0xffffffffu, my_w, j);                  // 0 for j >= cnt
-            const int n2 = __shfl_sync(0xffffffffu, my_n, (j + RING) & 31);
-            if (j + RING < cnt && act) ring[r] = *reinterpret_cast<const uint4*>(h + (int64_t)n2 * D + c);
+            const int n2 = __shfl_sync(0xffffffffu, my_n, min(j + RING, last));
+            ring[r] = *reinterpret_cast<const uint4*>(h + (int64_t)n2 * D + (act ? c : 0));
             float x[8];
             h8_to_float(v, x);
 #pragma unroll
@@ -507,169 +510,6 @@ spmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     row1 = row2;
     beg = beg1;
     end = end1;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// fp16-table SpMM with the gathered rows staged through shared memory by bulk async copies (TMA 1-D).
-// ncu r02a: the register-staged kernels above are bound by the latency of the row gathers -- long-scoreboard
-// stalls 57 %, DRAM 19 %, L2 26 %, issue 47 % -- and registers cap what can be in flight (8 rows x 512 B per warp:
-// ~64 KB per SM, i.e. ~1.5 us of effective latency at 12.6 G rows/s whatever the row width).  Here a warp issues the
-// 32 rows of an edge group as 32 `cp.async.bulk` copies (one per lane, completion on an mbarrier) into one of three
-// 16 KB shared-memory slots and consumes the group issued one tick earlier, while the (nbr, what) pairs of the group
-// after next are in flight in registers: up to 2 x 16 KB per warp, 128 KB per SM, with no register cost.
-// One warp per row (rows of more than SGS_HEAVY_ROW_DEG edges are left to the block-cooperative phase of the
-// register kernel, launched first).  Atomic-free, deterministic.
-// ---------------------------------------------------------------------------------------
-namespace bulk {
-constexpr int kWarps = 4;
-constexpr int kSlots = 3;
-constexpr int kSlotBytes = 32 * 512;                               // 32 rows of at most 256 fp16 columns
-constexpr int kSmemBytes = kWarps * kSlots * kSlotBytes + kWarps * kSlots * 8 + 128;
-__device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void bar_expect(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (spin > (1u << 26)) __trap();
-  }
-}
-}  // namespace bulk
-
-__global__ void __launch_bounds__(bulk::kWarps * 32, 1)
-spmm_h16_bulk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
-                     const float* __restrict__ what, const float* __restrict__ dis, const float* __restrict__ loopw,
-                     const __half* __restrict__ h, const float* __restrict__ tscale, int64_t N, int D,
-                     const float* __restrict__ bias, float* __restrict__ out, int flags, float p_drop, uint64_t seed,
-                     const int32_t* __restrict__ order, const SpmmPeers pe) {
-  using namespace bulk;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* wbuf = smem + (size_t)warp * kSlots * kSlotBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarps * kSlots * kSlotBytes) + warp * kSlots;
-  const uint32_t buf0 = s32(wbuf), bar0 = s32(bars);
-  if (lane == 0) {
-    for (int sidx = 0; sidx < kSlots; ++sidx) bar_init(bar0 + 8 * sidx, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const uint32_t thr = dropout_threshold(p_drop);
-  const float scale = (flags & SGS_SPMM_DROPOUT) ? 1.0f / (1.0f - p_drop) : 1.0f;
-  const float inv_scale = tscale[1];
-  const int n_heavy = order ? order[N] : 0;
-  const uint32_t rowb = (uint32_t)D * 2u;
-  const int c = lane * 8;
-  const bool act = c < D;
-
-  // ---- the warp's stream of edge groups: rows idx, idx + step, ... (heaviest first), 32 edges per group; a row
-  // without edges still yields one empty group so that its self term / bias are written.  Row metadata runs two rows
-  // ahead (order[] one row before rowptr[]), so the generator never waits on a dependent load ----
-  const int64_t step = (int64_t)gridDim.x * kWarps;
-  struct Desc { int base, cnt, last, slot; int64_t row; };
-  auto load_row = [&](int64_t i) -> int64_t { return i < N ? (order ? (int64_t)order[i] : i) : -1; };
-  int64_t i0 = (int64_t)n_heavy + (int64_t)blockIdx.x * kWarps + warp;
-  int64_t g_row = load_row(i0), g_row1 = load_row(i0 + step), g_row2 = load_row(i0 + 2 * step);
-  int64_t g_i2 = i0 + 2 * step;
-  int g_pos = 0, g_end = 0, g_beg1 = 0, g_end1 = 0;
-  if (g_row >= 0) { g_pos = rowptr[g_row]; g_end = rowptr[g_row + 1]; }
-  if (g_row1 >= 0) { g_beg1 = rowptr[g_row1]; g_end1 = rowptr[g_row1 + 1]; }
-  bool g_done = false;
-  auto advance_row = [&]() {
-    g_row = g_row1; g_pos = g_beg1; g_end = g_end1;
-    g_row1 = g_row2;
-    if (g_row1 >= 0) { g_beg1 = rowptr[g_row1]; g_end1 = rowptr[g_row1 + 1]; }
-    g_i2 += step;
-    g_row2 = load_row(g_i2);
-  };
-  auto gen = [&]() -> Desc {
-    Desc d;
-    d.slot = 0;
-    while (g_row >= 0 && (g_row < pe.row_lo || g_row >= pe.row_hi)) advance_row();   // rows of other ranks
-    if (g_row < 0) { d.base = 0; d.cnt = -1; d.last = 0; d.row = -1; g_done = true; return d; }   // stream exhausted
-    d.row = g_row;
-    d.base = g_pos;
-    d.cnt = max(0, min(32, g_end - g_pos));
-    g_pos += 32;
-    d.last = g_pos >= g_end;
-    if (d.last) advance_row();
-    return d;
-  };
-
-  SpmmRowH<1> r;
-  r.clear();
-  // pipeline registers: I stage (indices in flight), B stage (bulk copies issued), C stage (consumed)
-  Desc dI = gen();
-  int nI = 0; float wI = 0.f;
-  if (dI.cnt > 0 && lane < dI.cnt) { nI = nbr[dI.base + lane]; wI = what[dI.base + lane]; }
-  Desc dB; dB.cnt = -1; dB.last = 0; dB.row = -1; dB.base = 0; dB.slot = 0;
-  float wB = 0.f;
-  uint32_t issued = 0;   // bulk groups issued so far: slot = issued % kSlots, barrier parity = (issued / kSlots) & 1
-  while (true) {
-    // ---- B: issue the bulk copies of the group whose indices were fetched one tick ago ----
-    const Desc dC = dB;
-    const float wC = wB;
-    dB = dI;
-    wB = wI;
-    const int nB = nI;
-    if (dB.cnt > 0) {
-      const uint32_t sB = issued % kSlots;
-      dB.slot = (int)(sB | (((issued / kSlots) & 1u) << 8));
-      ++issued;
-      if (lane == 0) bar_expect(bar0 + 8 * sB, (uint32_t)dB.cnt * rowb);
-      __syncwarp();
-      if (lane < dB.cnt)
-        bulk_g2s(buf0 + sB * kSlotBytes + (uint32_t)lane * rowb, h + (int64_t)nB * D, rowb, bar0 + 8 * sB);
-    }
-    // ---- I: next descriptor, its (nbr, what) pairs go in flight ----
-    if (!g_done) {
-      dI = gen();
-      nI = 0; wI = 0.f;
-      if (dI.cnt > 0 && lane < dI.cnt) { nI = nbr[dI.base + lane]; wI = what[dI.base + lane]; }
-    } else {
-      dI.cnt = -1; dI.row = -1; dI.last = 0; dI.slot = 0;
-    }
-    // ---- C: consume the group issued at the previous tick ----
-    if (dC.cnt >= 0) {
-      if (dC.cnt > 0) {
-        const uint32_t sC = (uint32_t)dC.slot & 0xFFu;
-        bar_wait(bar0 + 8 * sC, ((uint32_t)dC.slot >> 8) & 1u);
-        const uint8_t* rows = wbuf + sC * kSlotBytes + c * 2;
-#pragma unroll 8
-        for (int j = 0; j < dC.cnt; ++j) {
-          const float wv = __shfl_sync(0xffffffffu, wC, j);
-          if (act) {
-            float x[8];
-            h8_to_float(*reinterpret_cast<const uint4*>(rows + (uint32_t)j * rowb), x);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) r.acc[0][t] = fmaf(wv, x[t], r.acc[0][t]);
-          }
-        }
-        __syncwarp();   // every lane has read the slot before a later tick's copies may overwrite it
-      }
-      if (dC.last) {
-        r.finish(dC.row, dis, loopw, h, D, lane, inv_scale, bias, out, flags, scale, thr, seed, pe);
-        r.clear();
-      }
-    } else if (dB.cnt < 0 && dI.cnt < 0) {
-      break;   // nothing in any stage
-    }
   }
 }
 
@@ -1007,28 +847,6 @@ static int32_t spmm_impl(const int32_t* rowptr, const int32_t* nbr, const float*
     if (pipe < 0) {
       const char* e = getenv("SGS_SPMM_PIPE");
       pipe = (e && e[0] == '1') ? 1 : 0;
-    }
-    // SGS_SPMM_BULK=1: rows staged through shared memory by bulk async copies (hub rows stay on the register kernel)
-    static int use_bulk = -1;
-    if (use_bulk < 0) {
-      const char* e = getenv("SGS_SPMM_BULK");
-      use_bulk = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (D <= 256 && use_bulk) {
-      SpmmPeers ph = pe;
-      ph.phases = 1;
-      spmm_h16_kernel<1, false><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D,
-                                                                bias, out, flags, p_drop, seed, order, ph);
-      SGS_LAUNCH_CHECK();
-      ph.phases = 2;
-      SGS_CUDA(cudaFuncSetAttribute(spmm_h16_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    bulk::kSmemBytes));
-      int64_t g = ceil_div(N, bulk::kWarps);
-      if (g > sm_count()) g = sm_count();
-      spmm_h16_bulk_kernel<<<(unsigned)g, bulk::kWarps * 32, bulk::kSmemBytes, st>>>(
-          rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D, bias, out, flags, p_drop, seed, order, ph);
-      SGS_LAUNCH_CHECK();
-      return SGS_OK;
     }
     if (D <= 256 && pipe)
       spmm_h16_kernel<1, true><<<row_grid(N), kBlock, 0, st>>>(rowptr, nbr, what, dis, loopw, hh, tscale, N, (int)D,

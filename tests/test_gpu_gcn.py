@@ -236,4 +236,7 @@ def test_degree_prior_kernel_matches_reference_formula(dev):
     datasets.add_degree(data)
     got = data.prob.cpu()
     assert got.shape == want.shape and abs(float(got.sum()) - 1.0) < 1e-4
-    assert float(((got - want).abs() / want).max()) < 1e-5
+    # the kernels accumulate the softmax normaliser in fp64, torch's CPU softmax in fp32: a uniform ~1e-5 relative
+    # offset of every entry (measured 1.5e-5 at E = 58 k), nothing edge-specific
+    rel = (got - want).abs() / want
+    assert float(rel.max()) < 1e-4 and float(rel.max() - rel.min()) < 2e-6

@@ -118,7 +118,7 @@ def test_add_degree_dropin_matches_oracle():
     if torch.cuda.is_available():      # host data: uploaded, computed by the kernels, copied back
         datasets.add_degree(d)
         want = ox.degree_prior(b.edge_index, b.num_nodes)
-        assert d.prob.device.type == "cpu" and float(((d.prob - want).abs() / want).max()) < 1e-5
+        assert d.prob.device.type == "cpu" and float(((d.prob - want).abs() / want).max()) < 1e-4
     else:                              # no GPU: fails loudly, there is no CPU implementation
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             datasets.add_degree(d)
