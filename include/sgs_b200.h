@@ -156,6 +156,15 @@ int32_t sgs_peer_push_rows(const float* src, const uint64_t* peer_bases, int32_t
                            int64_t row0, int64_t rows, int64_t D, int32_t include_self, sgs_stream_t stream);
 int32_t sgs_peer_reduce_rows(const uint64_t* peer_bases, int32_t world, int32_t rank, int64_t elem_off, int64_t row0,
                              int64_t rows, int64_t D, float* out, sgs_stream_t stream);
+/* Two GCN layers over the SAME graph in one gather pass: h16 is the fp16 table of [h_a | h_b] ([N, D], D = 2 x
+ * width), out_a / out_b receive the two [N, D/2] results (bias [D] = [b_a | b_b], one fused ReLU / dropout epilogue).
+ * The D = 256 SpMM is bound by the RATE of row gathers, not by their bytes (profiles/r02_notes.md), so the pair costs
+ * about one pass: the scorer's gcn1 and the random baseline's gcn1 (model.py:107, :159 over the same random subgraph,
+ * training_hybrid.py:45-48,93) share it. */
+int32_t sgs_spmm_h16_pair(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                          const float* dis, const float* loopw, const void* h16, const float* tscale, int64_t N,
+                          int64_t D, const float* bias, float* out_a, float* out_b, int32_t flags, float p_drop,
+                          uint64_t seed, sgs_stream_t stream);
 int32_t sgs_gcn_edge_grad_h16(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
                               const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
                               const int32_t* perm_src, const int32_t* src, const int32_t* dst, const float* G,

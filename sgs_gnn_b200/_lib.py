@@ -42,6 +42,7 @@ SIGNATURES = {
     "sgs_spmm_sharded": (I32, [P, P, P, P, P, P, P, P, P, I64, I64, P, P, I32, F32, U64, I64, I64, P, I32, I32, I64, P]),
     "sgs_peer_push_rows": (I32, [P, P, I32, I32, I64, I64, I64, I64, I32, P]),
     "sgs_peer_reduce_rows": (I32, [P, I32, I32, I64, I64, I64, I64, P, P]),
+    "sgs_spmm_h16_pair": (I32, [P, P, P, P, P, P, P, P, I64, I64, P, P, P, I32, F32, U64, P]),
     "sgs_gcn_edge_grad_h16": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, P]),
     "sgs_act_bwd": (I32, [P, P, I64, F32, P, P]),
     "sgs_colsum": (I32, [P, I64, I64, P, P]),

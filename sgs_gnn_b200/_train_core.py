@@ -88,7 +88,18 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     # pass 1: probabilities of ALL edges (training_hybrid.py:51-64), no autograd tape
     profiler = getattr(model, "gpu_profiler", None)
     ops.seg_begin(profiler, "edge_mlp_pre")
-    out = scorer.embed(batch.x, g_rand if g_rand is not None else g_full)
+    h_rand = None     # first layer of the random-baseline forward, when it shares the scorer's sweep (see below)
+    pair = (args.conditional and g_rand is not None and hasattr(scorer, "gcn2") and isinstance(scorer.gcn1, type(model.gcn1))
+            and float(model.dropout.p) == float(scorer.dropout.p)
+            and ops.gcn_conv_pair_available(batch.x, scorer.gcn1.lin.weight, model.gcn1.lin.weight))
+    if pair:
+        # scorer.gcn1 (model.py:107) and the random baseline's model.gcn1 (model.py:159 via training_hybrid.py:93) are
+        # both relu / dropout GCN layers over the SAME random subgraph and the same features: one gather sweep
+        h_e, h_rand = ops.gcn_conv_pair(batch.x, scorer.gcn1.lin.weight, scorer.gcn1.bias, model.gcn1.lin.weight,
+                                        model.gcn1.bias, g_rand, True, scorer._drop(), ops.next_seed())
+        out = scorer.gcn2(h_e, g_rand, None, relu=True)
+    else:
+        out = scorer.embed(batch.x, g_rand if g_rand is not None else g_full)
     ops.seg_end(profiler, "edge_mlp_pre")
     ops.seg_begin(profiler, "edge_score")
     seed_sc = ops.next_seed()
@@ -126,7 +137,7 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     random_out = None
     with_edges = bool(args.reg1 or args.reg2)
     if args.conditional:
-        random_out = model(batch, g_rand)
+        random_out = model.gcn2(h_rand, g_rand, None) if h_rand is not None else model(batch, g_rand)
         # calculate_f1 x2 (training_hybrid.py:94-95): micro-F1 == accuracy; same denominator, so the
         # strict `>` of :98 compares the two correct-counts.
         acc_l = ops.loss_forward(learned_out.detach(), batch.y, tm_u8, g_s if with_edges else None,

@@ -20,6 +20,8 @@ struct SpmmPeers {
   int64_t off;             // element offset of the destination buffer inside every arena
   int64_t row_lo, row_hi;  // owned row range
   int phases;              // bit 0: block-cooperative hub rows, bit 1: one warp per remaining row (3 = both)
+  float* out2;             // fp16-table form, pair mode: columns [split, D) go to out2 (both outputs [N, split])
+  int split;               // 0 = single output [N, D]
 };
 __device__ __forceinline__ void peer_store4(const SpmmPeers& pe, int64_t idx, const float4& v) {
   for (int g = 0; g < pe.world; ++g)
@@ -407,6 +409,9 @@ struct SpmmRowH {
     for (int k = 0; k < K; ++k) {
       const int c = (k * 32 + lane) * 8;
       if (c < D) {
+        if (pe.split) {   // pair mode: two [N, split] outputs (no ADD_ROOT / ACCUM / peer stores in this mode)
+          orow = (c < pe.split ? out + row * pe.split : pe.out2 + row * pe.split - pe.split);
+        }
         float v[8], self[8];
         if (dis) h8_to_float(*reinterpret_cast<const uint4*>(hr + c), self);
 #pragma unroll
@@ -888,7 +893,7 @@ int32_t sgs_spmm(const int32_t* rowptr, const int32_t* nbr, const float* what, c
   SGS_CHECK_ARG(N > 0 && D > 0 && D < (1 << 20), "bad sizes");
   SGS_CHECK_ARG(rowptr && h && out, "null pointer");
   SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
-  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N, 3};
+  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N, 3, nullptr, 0};
   return spmm_impl(rowptr, nbr, what, order, dis, loopw, h, nullptr, nullptr, N, D, bias, out, flags, p_drop, seed, pe,
                    as_stream(stream));
 }
@@ -906,7 +911,7 @@ int32_t sgs_spmm_sharded(const int32_t* rowptr, const int32_t* nbr, const float*
   SGS_CHECK_ARG(!peer_bases || (world >= 1 && rank >= 0 && rank < world && elem_off >= 0), "bad peer arguments");
   SGS_CHECK_ARG(!peer_bases || !h16 || elem_off % 4 == 0, "peer buffer offset must be a multiple of 4 floats");
   SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
-  const SpmmPeers pe = {peer_bases, world, rank, elem_off, row_lo, row_hi, 3};
+  const SpmmPeers pe = {peer_bases, world, rank, elem_off, row_lo, row_hi, 3, nullptr, 0};
   return spmm_impl(rowptr, nbr, what, order, dis, loopw, h, h16, tscale, N, D, bias, out, flags, p_drop, seed, pe,
                    as_stream(stream));
 }
@@ -941,8 +946,22 @@ int32_t sgs_spmm_h16(const int32_t* rowptr, const int32_t* nbr, const float* wha
   SGS_CHECK_ARG(rowptr && h16 && tscale && out, "null pointer");
   SGS_CHECK_ARG((((uintptr_t)h16 | (uintptr_t)out) & 15) == 0, "h16 / out must be 16-byte aligned");
   SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
-  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N, 3};
+  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N, 3, nullptr, 0};
   return spmm_impl(rowptr, nbr, what, order, dis, loopw, nullptr, h16, tscale, N, D, bias, out, flags, p_drop, seed,
+                   pe, as_stream(stream));
+}
+
+int32_t sgs_spmm_h16_pair(const int32_t* rowptr, const int32_t* nbr, const float* what, const int32_t* order,
+                          const float* dis, const float* loopw, const void* h16, const float* tscale, int64_t N,
+                          int64_t D, const float* bias, float* out_a, float* out_b, int32_t flags, float p_drop,
+                          uint64_t seed, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && D > 0 && D % 16 == 0 && D <= 512, "the pair SpMM needs D % 16 == 0 and D <= 512");
+  SGS_CHECK_ARG(rowptr && h16 && tscale && out_a && out_b, "null pointer");
+  SGS_CHECK_ARG((((uintptr_t)h16 | (uintptr_t)out_a | (uintptr_t)out_b) & 15) == 0, "16-byte alignment required");
+  SGS_CHECK_ARG(!(flags & (SGS_SPMM_ACCUM | SGS_SPMM_ADD_ROOT)), "ACCUM / ADD_ROOT are not available in pair mode");
+  SGS_CHECK_ARG(!(flags & SGS_SPMM_DROPOUT) || (p_drop >= 0.f && p_drop < 1.f), "p_drop must be in [0,1)");
+  const SpmmPeers pe = {nullptr, 1, 0, 0, 0, N, 3, out_b, (int)(D / 2)};
+  return spmm_impl(rowptr, nbr, what, order, dis, loopw, nullptr, h16, tscale, N, D, bias, out_a, flags, p_drop, seed,
                    pe, as_stream(stream));
 }
 

@@ -650,6 +650,77 @@ class GCNConvFn(torch.autograd.Function):
         return dx, dw, db, dew, None, None, None, None
 
 
+class GCNConvPairFn(torch.autograd.Function):
+    """Two unweighted GCNConv layers over the SAME graph and the SAME static input in one pass:
+        out_a = dropout(relu(A_hat (x Wa^T) + ba)),   out_b = dropout(relu(A_hat (x Wb^T) + bb)).
+    One stacked projection x [Wa; Wb]^T, one fp16 gather table [N, 2D], ONE SpMM sweep (sgs_spmm_h16_pair): the
+    gather kernels are bound by the rate of row gathers, not by their bytes, so the pair costs about one layer.
+    Used for the scorer's gcn1 and the random baseline's gcn1, which both see the random subgraph
+    (model.py:107 / :159, training_hybrid.py:45-48,93).  Backward: per half, the plain GCNConv backward."""
+
+    @staticmethod
+    def forward(ctx, x, wa, ba, wb, bb, graph, relu, p_drop, seed):
+        x = _req(x, torch.float32, "x")
+        wa, wb = _req(wa, torch.float32, "weight"), _req(wb, torch.float32, "weight")
+        ctx.set_materialize_grads(False)     # an unused half (e.g. the random baseline on a learned-wins step) costs nothing
+        norm = graph.norm(None)
+        d = wa.size(0)
+        h = linear_nt(x, torch.cat([wa, wb], 0), static_x=True)
+        tab = gather_table(h)
+        if tab is None:
+            raise RuntimeError("gcn_conv_pair needs the fp16 gather mode and a width with 2 * D % 16 == 0, 2 * D <= 512")
+        n = x.size(0)
+        out_a = torch.empty(n, d, dtype=torch.float32, device=x.device)
+        out_b = torch.empty_like(out_a)
+        rowptr, _perm, nbr, order = graph.csr_dst
+        flags = (SPMM_RELU if relu else 0) | (SPMM_DROPOUT if p_drop > 0 else 0)
+        bias = torch.cat([_req(ba, torch.float32, "bias"), _req(bb, torch.float32, "bias")])
+        with _timed(f"spmm_d{2 * d}_pair"):
+            check(lib().sgs_spmm_h16_pair(_p(rowptr), _p(nbr), _p(norm.what_dst), _p(order), _p(norm.dis),
+                                          _p(norm.loopw), _p(tab.data), _p(tab.scale), n, 2 * d, _p(bias), _p(out_a),
+                                          _p(out_b), flags, float(p_drop), int(seed), _stream()), "sgs_spmm_h16_pair")
+        ctx.graph, ctx.norm, ctx.relu, ctx.p_drop = graph, norm, relu, p_drop
+        ctx.save_for_backward(x, out_a if relu else None, out_b if relu else None)
+        return out_a, out_b
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        x, out_a, out_b = ctx.saved_tensors
+        graph, norm = ctx.graph, ctx.norm
+        res = []
+        for gout, out, (need_w, need_b) in ((ga, out_a, ctx.needs_input_grad[1:3]), (gb, out_b, ctx.needs_input_grad[3:5])):
+            dw = db = None
+            if gout is not None and (need_w or need_b):
+                n, d = gout.shape
+                gout = _req(gout, torch.float32, "grad")
+                g = gout
+                if ctx.relu:
+                    g = torch.empty_like(gout)
+                    scale = 1.0 / (1.0 - ctx.p_drop) if ctx.p_drop > 0 else 1.0
+                    check(lib().sgs_act_bwd(_p(gout), _p(out), gout.numel(), scale, _p(g), _stream()), "sgs_act_bwd")
+                if need_b:
+                    db = torch.empty(d, dtype=torch.float32, device=g.device)
+                    check(lib().sgs_colsum(_p(g), n, d, _p(db), _stream()), "sgs_colsum")
+                if need_w:
+                    dh = spmm(graph.csr_src, norm.what_src, norm, g, table=gather_table(g, scaled=True))
+                    dw = gemm_tn(dh, x, static_b=True)
+            res += [dw, db]
+        return (None, res[0], res[1], res[2], res[3], None, None, None, None)
+
+
+def gcn_conv_pair_available(x, wa, wb):
+    """The one-sweep pair applies in the fp16 gather mode, for a static input and equal widths with 2 D <= 512."""
+    d = wa.size(0)
+    if __import__("os").environ.get("SGS_NO_PAIR"):      # A/B switch
+        return False
+    return (_state["gather"] == PREC_FP16 and not x.requires_grad and wa.shape == wb.shape and (2 * d) % 16 == 0
+            and 128 <= 2 * d <= 512 and (x.size(0) * 2 * d) % 8 == 0)
+
+
+def gcn_conv_pair(x, wa, ba, wb, bb, graph, relu=False, p_drop=0.0, seed=0):
+    return GCNConvPairFn.apply(x, wa, ba, wb, bb, graph, relu, float(p_drop), int(seed))
+
+
 def gcn_conv(x, weight, bias, graph, edge_weight=None, relu=False, p_drop=0.0, seed=0):
     return GCNConvFn.apply(x, weight, bias, edge_weight, graph, relu, float(p_drop), int(seed))
 

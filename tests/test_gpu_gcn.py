@@ -240,3 +240,37 @@ def test_degree_prior_kernel_matches_reference_formula(dev):
     # offset of every entry (measured 1.5e-5 at E = 58 k), nothing edge-specific
     rel = (got - want).abs() / want
     assert float(rel.max()) < 1e-4 and float(rel.max() - rel.min()) < 2e-6
+
+
+def test_gcn_conv_pair_equals_two_layers(dev):
+    """ops.gcn_conv_pair (two GCN layers over one graph in ONE gather sweep) against two separate gcn_conv calls:
+    forward bit-identical sums (same table values, same accumulation order), gradients of either half equal to the
+    plain layer's."""
+    from sgs_gnn_b200 import ops, synth
+    b = synth.make_graph(None, seed=12, n=3000, e=90000, f=48, c=4).to(dev)
+    g = ops.graph_of(b.edge_index, 3000)
+    gen = torch.Generator(device=dev).manual_seed(4)
+    ws = [torch.randn(256, 48, generator=gen, device=dev) * 0.1 for _ in range(2)]
+    bs = [torch.randn(256, generator=gen, device=dev) * 0.1 for _ in range(2)]
+    gouts = [torch.randn(3000, 256, generator=gen, device=dev) for _ in range(2)]
+    before = ops.get_precision()
+    try:
+        ops.set_precision(gather="fp16")
+        assert ops.gcn_conv_pair_available(b.x, ws[0], ws[1])
+        pa = [t_.clone().requires_grad_(True) for t_ in (ws[0], bs[0], ws[1], bs[1])]
+        oa, ob = ops.gcn_conv_pair(b.x, pa[0], pa[1], pa[2], pa[3], g, True, 0.0, 0)
+        ref = []
+        for i in range(2):
+            w_, b_ = ws[i].clone().requires_grad_(True), bs[i].clone().requires_grad_(True)
+            o = ops.gcn_conv(b.x, w_, b_, g, None, relu=True)
+            o.backward(gouts[i])
+            ref.append((o.detach(), w_.grad, b_.grad))
+        assert float((oa - ref[0][0]).abs().max()) <= 1e-6 * float(ref[0][0].abs().max())
+        assert float((ob - ref[1][0]).abs().max()) <= 1e-6 * float(ref[1][0].abs().max())
+        # only the second half is back-propagated (a random-wins step): the first half's parameters keep grad None
+        ob.backward(gouts[1])
+        assert pa[0].grad is None and pa[1].grad is None
+        rel = lambda a, c: float((a - c).abs().max() / (c.abs().max() + 1e-30))   # noqa: E731
+        assert rel(pa[2].grad, ref[1][1]) < 1e-4 and rel(pa[3].grad, ref[1][2]) < 1e-4
+    finally:
+        ops.set_precision(**before)
