@@ -448,16 +448,17 @@ def _rows_aligned16(t, cache=False):
 _lin_cache = {}
 
 
-def linear_nt(x, w, precision=None, static_x=False):
+def linear_nt(x, w, precision=None, static_x=False, remember=True):
     """x[M,K] @ w[N,K]^T.  static_x (node features): the product is remembered until `w` changes -- the learned and
     the random-baseline forward of one step apply the same gcn1 weight to the same features (training_hybrid.py:88,93),
-    so the second projection (and its gather table) is free."""
+    so the second projection (and its gather table) is free.  remember=False for a caller that writes into the
+    result (the returned tensor is then private to it)."""
     x = _req(x, torch.float32, "x")
     w = _req(w, torch.float32, "weight")
     prec = _state["gemm"] if precision is None else precision
     m, k, n = x.size(0), x.size(1), w.size(0)
     key = None
-    if static_x:
+    if static_x and remember:
         key = (id(x), id(w))
         hit = _lin_cache.get(key)
         if hit is not None and hit[0]() is x and hit[1]() is w and hit[2] == (x._version, w._version, prec):
@@ -756,7 +757,8 @@ class SAGEConvFn(torch.autograd.Function):
         w_dst, _ = SAGEConvFn._mean_weights(graph)
         static = not x.requires_grad
         h_l = linear_nt(x, _req(w_l, torch.float32, "lin_l.weight"), static_x=static)
-        out = linear_nt(x, _req(w_r, torch.float32, "lin_r.weight"), static_x=static)   # root term
+        out = linear_nt(x, _req(w_r, torch.float32, "lin_r.weight"), static_x=static, remember=False)   # root term,
+        # accumulated into by the SpMM below
         spmm(graph.csr_dst, w_dst, None, h_l, _req(b_l, torch.float32, "lin_l.bias"), relu, p_drop, seed, out=out,
              add_root=True)
         ctx.graph, ctx.relu, ctx.p_drop = graph, relu, p_drop
