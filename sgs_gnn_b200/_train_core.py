@@ -89,7 +89,10 @@ def learned_step(pipeline, args, epoch, max_epoch, model, batch, criterion, q, b
     profiler = getattr(model, "gpu_profiler", None)
     ops.seg_begin(profiler, "edge_mlp_pre")
     h_rand = None     # first layer of the random-baseline forward, when it shares the scorer's sweep (see below)
-    pair = (args.conditional and g_rand is not None and hasattr(scorer, "gcn2") and isinstance(scorer.gcn1, type(model.gcn1))
+    # (opt-in, SGS_PAIR=1: measured neutral on the Reddit shape once the D = 256 gather was software-pipelined --
+    # 3.66 ms for the D = 512 pair sweep vs 2 x 1.5 ms -- see profiles/r02_notes.md)
+    pair = (bool(__import__("os").environ.get("SGS_PAIR")) and args.conditional and g_rand is not None
+            and hasattr(scorer, "gcn2") and isinstance(scorer.gcn1, type(model.gcn1))
             and float(model.dropout.p) == float(scorer.dropout.p)
             and ops.gcn_conv_pair_available(batch.x, scorer.gcn1.lin.weight, model.gcn1.lin.weight))
     if pair:

@@ -122,7 +122,7 @@ struct SpmmRow {
         my_w = what[base + lane];
       }
       const int cnt = min(32, end - base);
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < cnt; ++j) {
         const int n = __shfl_sync(0xffffffffu, my_n, j);
         const float wv = __shfl_sync(0xffffffffu, my_w, j);
@@ -581,22 +581,25 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   // g_e, t_e of the edges [beg, end) of the current row; returns sum t_e (valid in every lane)
   auto edges = [&](int beg, int end) {
     float tsum = 0.f;
-    // four neighbours per iteration: their row loads and shuffle reductions are independent (ILP)
+    // eight neighbours per iteration: their row loads and shuffle reductions are independent (the kernel is bound by
+    // the latency of the row gathers)
     int i = beg;
-    for (; i + 4 <= end; i += 4) {
-      float d0 = partial_dot(h + (int64_t)nbr[i] * D);
-      float d1 = partial_dot(h + (int64_t)nbr[i + 1] * D);
-      float d2 = partial_dot(h + (int64_t)nbr[i + 2] * D);
-      float d3 = partial_dot(h + (int64_t)nbr[i + 3] * D);
+    for (; i + 8 <= end; i += 8) {
+      const float* hp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) hp[u] = h + (int64_t)nbr[i + u] * D;
+      float d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) d[u] = partial_dot(hp[u]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
       }
-      if (lane < 4) {
-        const float g = lane == 0 ? d0 : (lane == 1 ? d1 : (lane == 2 ? d2 : d3));
+      if (lane < 8) {
+        float g = d[0];
+#pragma unroll
+        for (int u = 1; u < 8; ++u) g = lane == u ? d[u] : g;
         const int e = perm[i + lane];
         const float t = g * what[i + lane];
         tmp_g[e] = g;
@@ -616,6 +619,7 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     }
     tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
     tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
     return __shfl_sync(0xffffffffu, tsum, 0);
   };
   auto finish = [&](int64_t row, float tsum) {
@@ -632,7 +636,7 @@ edge_grad_sddmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     const int64_t row = order[hidx];
     load_row(row);
     const int beg = rowptr[row], end = rowptr[row + 1];
-    const int per = (((end - beg) + kWarpsPerBlock - 1) / kWarpsPerBlock + 3) & ~3;
+    const int per = (((end - beg) + kWarpsPerBlock - 1) / kWarpsPerBlock + 7) & ~7;
     const int b = min(end, beg + warp * per), e = min(end, b + per);
     const float part = edges(b, e);
     if (lane == 0) red[warp] = part;
@@ -703,21 +707,26 @@ edge_grad_sddmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __
   auto dot_with = [&](const __half* hp) { return warp_sum(partial_dot(hp)); };
   auto edges = [&](int beg, int end) {
     float tsum = 0.f;
+    // eight neighbours per iteration: their row loads are all issued before the first dot product is reduced
+    // (the kernel is bound by the latency of these gathers, ncu r02a: long-scoreboard stalls), then eight
+    // interleaved shuffle reductions
     int i = beg;
-    for (; i + 4 <= end; i += 4) {
-      float d0 = partial_dot(h + (int64_t)nbr[i] * D);
-      float d1 = partial_dot(h + (int64_t)nbr[i + 1] * D);
-      float d2 = partial_dot(h + (int64_t)nbr[i + 2] * D);
-      float d3 = partial_dot(h + (int64_t)nbr[i + 3] * D);
+    for (; i + 8 <= end; i += 8) {
+      const __half* hp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) hp[u] = h + (int64_t)nbr[i + u] * D;
+      float d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) d[u] = partial_dot(hp[u]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
       }
-      if (lane < 4) {
-        const float g = lane == 0 ? d0 : (lane == 1 ? d1 : (lane == 2 ? d2 : d3));
+      if (lane < 8) {
+        float g = d[0];
+#pragma unroll
+        for (int u = 1; u < 8; ++u) g = lane == u ? d[u] : g;
         const int e = perm[i + lane];
         const float t = g * what[i + lane];
         tmp_g[e] = g;
@@ -737,6 +746,7 @@ edge_grad_sddmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __
     }
     tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
     tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
     return __shfl_sync(0xffffffffu, tsum, 0);
   };
   auto finish = [&](int64_t row, float tsum) {
@@ -751,7 +761,7 @@ edge_grad_sddmm_h16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __
     const int64_t row = order[hidx];
     load_row(row);
     const int beg = rowptr[row], end = rowptr[row + 1];
-    const int per = (((end - beg) + kWarpsPerBlock - 1) / kWarpsPerBlock + 3) & ~3;
+    const int per = (((end - beg) + kWarpsPerBlock - 1) / kWarpsPerBlock + 7) & ~7;
     const int b = min(end, beg + warp * per), e = min(end, b + per);
     const float part = edges(b, e);
     if (lane == 0) red[warp] = part;
