@@ -318,7 +318,8 @@ constexpr int NSTAGE = 3;
 constexpr int EPI_WARP0 = 2;
 constexpr int EPI_GROUPS = 4;
 constexpr int THREADS = (EPI_WARP0 + 4 * EPI_GROUPS) * 32;   // 576
-constexpr int CHUNK = 8;                       // edges per epilogue chunk
+constexpr int CHUNK = 4;                       // edges per epilogue chunk
+constexpr int AHEAD = 3;                       // chunks of x / y gathers in flight ahead of the chunk being reduced
 }  // namespace kbf
 
 template <typename T>
@@ -330,6 +331,13 @@ __device__ __forceinline__ float tab_to_float<__nv_bfloat16>(unsigned short u) {
   return __uint_as_float((uint32_t)u << 16);
 }
 
+// 32 lanes x 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
 // 32 lanes x 8 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -514,12 +522,14 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
     uint32_t lt = tb;
     for (int64_t t = tile0 + tb * tstep; t < ntiles; t += 2 * tstep, lt += 2) {
       mbar_wait(epfull0 + 8 * tb, (lt >> 1) & 1);
-      // software pipeline over chunks of CHUNK edges: the endpoints and the x / y gathers of chunk ch + 1 are
-      // issued before chunk ch is reduced, so the gather latency overlaps the FMAs / REDs of the previous chunk
+      // software pipeline over chunks of CHUNK edges: the x / y gathers of the next AHEAD chunks are in flight while
+      // chunk ch is reduced.  The epilogue is bound by the latency of these 2-byte gathers (ncu r02a: long-scoreboard
+      // 51 %; tile time = chunks x latency / lookahead), so the lookahead distance is what sets BF's duration: 4 chunks
+      // of 4 edges (16 edges ahead, 32 loads in flight per thread) in the registers that 2 chunks of 8 used before.
       constexpr int NCH = 64 / CHUNK;
-      // (the endpoints are re-read from shared memory when a chunk is reduced: one LDS.64 per edge is cheaper than
-      // keeping two chunks of them in registers -- 96 registers per thread, see above)
-      unsigned short xv[2][CHUNK], yv[2][CHUNK];
+      constexpr int NBUF = AHEAD + 1;
+      static_assert(CHUNK == 4, "tmem_ld4 below");
+      unsigned short xv[NBUF][CHUNK], yv[NBUF][CHUNK];
       auto issue = [&](int ch, unsigned short* xc, unsigned short* yc) {
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) {
@@ -528,7 +538,8 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
           yc[j] = __ldg(reinterpret_cast<const unsigned short*>(tabb + (uint32_t)sd.y * ROWB2));
         }
       };
-      issue(0, xv[0], yv[0]);
+#pragma unroll
+      for (int a = 0; a < AHEAD; ++a) issue(a, xv[a], yv[a]);
       uint32_t cur_s = (uint32_t)ep[0].x;           // never flagged (first edge of the half)
       float xcur = tab_to_float<T>(xv[0][0]);
       float acc = 0.f;                              // S-scaled source-side run sum
@@ -536,11 +547,11 @@ edge_score_bwd_df_kernel(const __grid_constant__ CUtensorMap map_g, const T* __r
       tc_fence_after();
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        const int cb = ch & 1;
+        const int cb = ch % NBUF;
         uint32_t f1[CHUNK], f2[CHUNK];
-        tmem_ld8(taddr0 + ch * CHUNK, f1);
-        tmem_ld8(taddr0 + 128 + ch * CHUNK, f2);
-        if (ch + 1 < NCH) issue(ch + 1, xv[cb ^ 1], yv[cb ^ 1]);
+        tmem_ld4(taddr0 + ch * CHUNK, f1);
+        tmem_ld4(taddr0 + 128 + ch * CHUNK, f2);
+        if (ch + AHEAD < NCH) issue(ch + AHEAD, xv[(ch + AHEAD) % NBUF], yv[(ch + AHEAD) % NBUF]);
         tmem_ld_wait();
         int2 sd[CHUNK];
 #pragma unroll
