@@ -27,6 +27,26 @@ __global__ void push_rows_kernel(const float4* __restrict__ src, const uint64_t*
     dstp[i] = src[i];
 }
 
+// scalar forms for slabs that are not 16-byte aligned / not a multiple of 4 floats (the [N, 41] logits, [N, 3] norm
+// statistics: a few MB, latency-bound anyway)
+__global__ void push_rows_scalar_kernel(const float* __restrict__ src, const uint64_t* __restrict__ peer_bases,
+                                        int world, int rank, int64_t elem_off, int64_t n, int include_self) {
+  const int g = blockIdx.y;
+  if (g == rank && !include_self) return;
+  float* dstp = reinterpret_cast<float*>(peer_bases[g] + (uint64_t)elem_off * sizeof(float));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dstp[i] = src[i];
+}
+__global__ void reduce_rows_scalar_kernel(const uint64_t* __restrict__ peer_bases, int world, int rank,
+                                          int64_t elem_off, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int g = 0; g < world; ++g)
+      acc += reinterpret_cast<const float*>(peer_bases[g] + (uint64_t)elem_off * sizeof(float))[i];
+    out[i] = acc;
+  }
+}
+
 __global__ void reduce_rows_kernel(const uint64_t* __restrict__ peer_bases, int world, int rank, int64_t elem_off,
                                    int64_t n4, float4* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -54,11 +74,18 @@ int32_t sgs_peer_push_rows(const float* src, const uint64_t* peer_bases, int32_t
   SGS_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && rows >= 0 && D > 0 && row0 >= 0, "bad arguments");
   if (rows == 0) return SGS_OK;
   SGS_CHECK_ARG(src && peer_bases, "null pointer");
-  SGS_CHECK_ARG((rows * D) % 4 == 0 && ((elem_off + row0 * D) % 4) == 0 && ((uintptr_t)src & 15) == 0,
-                "slab must be 16-byte aligned and a multiple of 4 floats");
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if ((rows * D) % 4 != 0 || ((elem_off + row0 * D) % 4) != 0 || ((uintptr_t)src & 15) != 0) {
+    const int64_t n = rows * D;
+    int64_t gs = ceil_div(n, 256);
+    dim3 grid_s((unsigned)(gs > cap ? cap : gs), (unsigned)world);
+    push_rows_scalar_kernel<<<grid_s, 256, 0, as_stream(stream)>>>(src, peer_bases, world, rank, elem_off + row0 * D, n,
+                                                                   include_self);
+    SGS_LAUNCH_CHECK();
+    return SGS_OK;
+  }
   const int64_t n4 = rows * D / 4;
   int64_t g = ceil_div(n4, 256);
-  const int64_t cap = (int64_t)sm_count() * 4;
   dim3 grid((unsigned)(g > cap ? cap : g), (unsigned)world);
   push_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src), peer_bases, world, rank,
                                                         elem_off + row0 * D, n4, include_self);
@@ -71,11 +98,17 @@ int32_t sgs_peer_reduce_rows(const uint64_t* peer_bases, int32_t world, int32_t 
   SGS_CHECK_ARG(world >= 1 && rows >= 0 && D > 0 && row0 >= 0, "bad arguments");
   if (rows == 0) return SGS_OK;
   SGS_CHECK_ARG(out && peer_bases, "null pointer");
-  SGS_CHECK_ARG((rows * D) % 4 == 0 && ((elem_off + row0 * D) % 4) == 0 && ((uintptr_t)out & 15) == 0,
-                "slab must be 16-byte aligned and a multiple of 4 floats");
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if ((rows * D) % 4 != 0 || ((elem_off + row0 * D) % 4) != 0 || ((uintptr_t)out & 15) != 0) {
+    const int64_t n = rows * D;
+    int64_t gs = ceil_div(n, 256);
+    reduce_rows_scalar_kernel<<<(unsigned)(gs > cap ? cap : gs), 256, 0, as_stream(stream)>>>(
+        peer_bases, world, rank, elem_off + row0 * D, n, out);
+    SGS_LAUNCH_CHECK();
+    return SGS_OK;
+  }
   const int64_t n4 = rows * D / 4;
   int64_t g = ceil_div(n4, 256);
-  const int64_t cap = (int64_t)sm_count() * 8;
   reduce_rows_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, as_stream(stream)>>>(
       peer_bases, world, rank, elem_off + row0 * D, n4, reinterpret_cast<float4*>(out));
   SGS_LAUNCH_CHECK();

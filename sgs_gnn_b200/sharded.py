@@ -102,9 +102,8 @@ class Comm:
 
     # ---- peer-memory slab exchange ----
     def peer_stage(self, n, d):
-        """Destination of a fused slab all-gather: (stage view, elem_off) or None when peer memory is not in use
-        (d % 4 != 0 rows cannot be moved as float4)."""
-        if self.peer is None or (n * d) % 4 or d % 4:
+        """Destination of a fused slab all-gather: (stage view, elem_off) or None when peer memory is not in use."""
+        if self.peer is None:
             return None
         return self.peer.region("stage", n, d)
 
@@ -140,6 +139,18 @@ class Comm:
 
     def all_reduce(self, t):
         if self.world == 1:
+            return t
+        if self.peer is not None and t.dtype == torch.float32 and t.numel() >= 4096 and t.is_contiguous():
+            # fp32 vectors (the edge-weight gradient's per-node sums, the flat weight gradients): every rank leaves its
+            # copy in the arena and sums all `world` copies itself with peer loads -- a latency-bound NCCL ring of 8
+            # becomes copy + barrier + one reduction kernel
+            n = t.numel()
+            part, off = self.peer.region("part", n, 1)
+            with _timed("comm_allreduce"):
+                part.view(-1).copy_(t.reshape(-1))
+                self.peer.barrier()
+                check(lib().sgs_peer_reduce_rows(self.peer.bases, self.world, self.rank, off, 0, n, 1,
+                                                 _p(t), _stream()), "sgs_peer_reduce_rows")
             return t
         with _timed("comm_allreduce"):
             if self.staged and t.is_cuda:
@@ -201,7 +212,7 @@ class Comm:
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         if self.world == 1:
             return full[lo:hi]
-        if (self.peer is not None and full.dim() == 2 and full.dtype == torch.float32 and full.size(1) % 4 == 0):
+        if self.peer is not None and full.dim() == 2 and full.dtype == torch.float32:
             part, off = self.peer.region("part", full.size(0), full.size(1))
             with _timed("comm_reduce"):
                 part.copy_(full)
@@ -494,7 +505,7 @@ class ShardedGCNConvFn(torch.autograd.Function):
                 check(lib().sgs_colsum(_p(g_full[lo:hi]), ns, d, _p(db), _stream()), "sgs_colsum")
         if need_w or need_x:
             tab_g = ops.gather_table(g_full, scaled=True)
-            if comm.peer is not None and d % 4 == 0 and comm.world > 1:
+            if comm.peer is not None and comm.world > 1:
                 # partial sums for arbitrary rows, left in the symmetric arena and summed with peer loads
                 part, off = comm.peer.region("part", n, d)
                 ops.spmm(g.csr_src, norm.what_src, norm, g_full, table=tab_g, out=part)
