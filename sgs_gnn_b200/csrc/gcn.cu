@@ -81,7 +81,25 @@ gcn_what_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   for (; row < N; row += step) {
     int beg = rowptr[row], end = rowptr[row + 1];
     float dr = dis[row];
-    for (int i = beg + lane; i < end; i += 32) {
+    // four 32-edge groups per iteration: the dependent gathers dis[nbr], w[perm] of all four are in flight together
+    int i = beg + lane;
+    for (; i + 96 < end; i += 128) {
+      int s[4], e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] = nbr[i + 32 * u];
+        e[u] = w ? perm[i + 32 * u] : 0;
+      }
+      float ds[4], we[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ds[u] = dis[s[u]];
+        we[u] = w ? w[e[u]] : 1.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) what[i + 32 * u] = (s[u] == (int)row) ? 0.f : (ds[u] * we[u]) * dr;
+    }
+    for (; i < end; i += 32) {
       int s = nbr[i];
       float we = w ? w[perm[i]] : 1.0f;
       what[i] = (s == (int)row) ? 0.f : (dis[s] * we) * dr;

@@ -1,5 +1,7 @@
 // K5: fused cross-entropy + accuracy (conditional gate) + assortative BCE (reg1) + consistency MSE
 // (reg2), forward and backward.  One pass over the train rows and one over the sampled edges.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sgs {
@@ -219,14 +221,13 @@ __global__ void node_code_kernel(const int64_t* __restrict__ y, const uint8_t* _
   for (; n < N; n += step) code[n] = train_mask[n] ? (int32_t)y[n] : -1;
 }
 
-template <int KC>   // columns per lane: C <= 16 * KC
+template <int KC, int UN>   // KC columns per lane (C <= 16 * KC); UN destination rows in flight
 __global__ void __launch_bounds__(kThreads)
 loss_edges_fused_kernel(const float* __restrict__ logits, int C, const int32_t* __restrict__ code,
                         const int32_t* __restrict__ s_src, const int32_t* __restrict__ s_dst,
                         const float* __restrict__ p_s, int64_t q, double* __restrict__ acc,
                         float* __restrict__ dlog_e, float* __restrict__ u1, float* __restrict__ u2) {
   constexpr int RUN = 16;   // consecutive edges per 16-lane group and iteration
-  constexpr int UN = 4;     // destination rows in flight
   const int sl = threadIdx.x & 15;
   const uint32_t hm = 0xFFFFu << (threadIdx.x & 16);   // this half-warp
   int64_t grp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 4;
@@ -462,9 +463,21 @@ int32_t sgs_loss_fwd_fused(const float* logits, int64_t N, int64_t C, const int6
   node_code_kernel<<<lgrid(kThreads, N), kThreads, 0, st>>>(y, train_mask, N, node_code);
   SGS_LAUNCH_CHECK();
   const int grid = lgrid(kThreads, q);   // 16 groups of 16 edges per block and iteration
-#define SGS_LEF(KC)                                                                                              \
-  loss_edges_fused_kernel<KC><<<grid, kThreads, 0, st>>>(logits, (int)C, node_code, s_src, s_dst, p_s, q, acc, \
-                                                         dlog_e, u_reg1, u_reg2)
+  // SGS_LOSS_UN=8: eight destination rows in flight per 16-lane group instead of four (A/B switch)
+  static int un8 = -1;
+  if (un8 < 0) {
+    const char* e = getenv("SGS_LOSS_UN");
+    un8 = (e && e[0] == '8') ? 1 : 0;
+  }
+#define SGS_LEF(KC)                                                                                                 \
+  do {                                                                                                              \
+    if (un8)                                                                                                        \
+      loss_edges_fused_kernel<KC, 8><<<grid, kThreads, 0, st>>>(logits, (int)C, node_code, s_src, s_dst, p_s, q,    \
+                                                                acc, dlog_e, u_reg1, u_reg2);                       \
+    else                                                                                                            \
+      loss_edges_fused_kernel<KC, 4><<<grid, kThreads, 0, st>>>(logits, (int)C, node_code, s_src, s_dst, p_s, q,    \
+                                                                acc, dlog_e, u_reg1, u_reg2);                       \
+  } while (0)
   if (C <= 16) SGS_LEF(1);
   else if (C <= 32) SGS_LEF(2);
   else if (C <= 48) SGS_LEF(3);
