@@ -56,7 +56,12 @@ def peaks():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons of this rank's GPU, sampled every 100 ms by a child process that is
+    started BEFORE the warm-up (its start-up takes longer than a short timed region on an 8-GPU box).  Every sample
+    carries nvidia-smi's own timestamp; summary() keeps the samples that fall inside the timed region
+    (`window: "timed"`), and only if the region was too short to contain one, the samples of the identical
+    warm-up steps of the 3 s before it (`window: "warmup+timed"`)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -64,19 +69,38 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
-        if os.environ.get("SGS_NO_CLOCKS"):
+        if os.environ.get("SGS_NO_CLOCKS") or self.index is None:
             return self
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
         return self
+
+    def wait_ready(self, timeout=8.0):
+        """Block (before the timed region) until the child has written its first sample."""
+        t_end = time.time() + timeout
+        while self.proc is not None and self.proc.poll() is None and time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.05)
+        return False
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -86,29 +110,44 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.path or not os.path.isfile(self.path):
             return out
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                rows.append((self._stamp(parts[0]), float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nme, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        t0, t1 = self.t0, self.t1
+        window = "timed"
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if r[0] is not None and t0 <= r[0] <= t1 + 0.05]
+            if not inside:      # timed region shorter than one sampling period: the identical steps just before it
+                inside = [r for r in rows if r[0] is not None and t0 - 3.0 <= r[0] <= t1 + 0.05]
+                window = "warmup+timed"
+        else:
+            inside = rows
+        if inside:
+            out["sm_mhz"] = statistics.median(r[1] for r in inside)
+            out["sm_max_mhz"] = max(r[2] for r in inside)
+            out["samples"] = len(inside)
+            out["window"] = window
+            out["reasons"] = sorted({n for r in inside for n in r[3]})
         try:
             os.unlink(self.path)
         except OSError:
@@ -328,6 +367,8 @@ def run_gpu_arm(a):
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(gemm=a.gemm_precision, scorer=a.precision, gather=a.gather_precision)
     _lib.lib()
+    # rank 0's GPU is the one reported; started here because nvidia-smi needs seconds to come up on an 8-GPU box
+    clk = ClockSampler(local if rank == 0 else None).__enter__()
 
     shard = world > 1 and a.parallel == "shard" and not a.clusters
     clusters = None
@@ -395,6 +436,7 @@ def run_gpu_arm(a):
         epoch(loader, 1 + w)
     # a fresh box pages the image in for its first seconds: keep warming (untimed) until two consecutive epochs
     # agree within 5% (at most 6 extra), so start-up noise of the host does not land in the timed steps
+    clk.wait_ready()      # (before the last warm-up epochs, so the timed steps start on a busy GPU)
     extra, last = 0, None
     while extra < 6 and not profiling_env():
         t0 = time.perf_counter()
@@ -424,13 +466,14 @@ def run_gpu_arm(a):
         from torch.profiler import ProfilerActivity, profile
         tprof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
         tprof.__enter__()
-    with ClockSampler(local) as clk, ops.KernelTimer() as kt:
+    with clk, ops.KernelTimer() as kt:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cprof = None
         if os.environ.get("SGS_CPROFILE"):     # debug aid: host-side cost of a step
             import cProfile
             cprof = cProfile.Profile()
             cprof.enable()
+        clk.begin()
         ev0.record()
         for s in range(a.steps):
             t_s = time.perf_counter()
@@ -448,6 +491,7 @@ def run_gpu_arm(a):
             pstats.Stats(cprof, stream=buf).sort_stats("tottime").print_stats(45)
             open(os.environ["SGS_CPROFILE"] + f".rank{rank}.txt", "w").write(buf.getvalue())
         barrier()
+        clk.end()
         if profiling:
             torch.cuda.cudart().cudaProfilerStop()
         ms = ev0.elapsed_time(ev1)

@@ -196,6 +196,14 @@ int32_t sgs_gcn_edge_grad_partial(const int32_t* rowptr_dst, const int32_t* perm
                                   const int32_t* perm_src, const float* G, const float* h,
                                   const float* dis, const float* loopw, int64_t M, int64_t N, int64_t D,
                                   float* tmp_g, float* tmp_t, float* tmp_a, sgs_stream_t stream);
+/* _partial with the rows of h gathered from its fp16 table (sgs_table_f16), as sgs_gcn_edge_grad_h16 does. */
+int32_t sgs_gcn_edge_grad_partial_h16(const int32_t* rowptr_dst, const int32_t* perm_dst,
+                                      const int32_t* nbr_dst, const float* what_dst,
+                                      const int32_t* order_dst /* may be NULL */, const int32_t* rowptr_src,
+                                      const int32_t* perm_src, const float* G, const void* h16,
+                                      const float* tscale, const float* dis, const float* loopw, int64_t M,
+                                      int64_t N, int64_t D, float* tmp_g, float* tmp_t, float* tmp_a,
+                                      sgs_stream_t stream);
 int32_t sgs_gcn_edge_grad_final(const int32_t* src, const int32_t* dst, const float* tmp_g,
                                 const float* tmp_a, const float* dis, const float* deg, int64_t M,
                                 float* dw, int32_t accumulate, sgs_stream_t stream);

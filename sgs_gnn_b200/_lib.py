@@ -48,6 +48,7 @@ SIGNATURES = {
     "sgs_colsum": (I32, [P, I64, I64, P, P]),
     "sgs_gcn_edge_grad": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, P]),
     "sgs_gcn_edge_grad_partial": (I32, [P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P]),
+    "sgs_gcn_edge_grad_partial_h16": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, P, P]),
     "sgs_gcn_edge_grad_final": (I32, [P, P, P, P, P, P, I64, P, I32, P]),
     "sgs_round_tf32": (I32, [P, I64, P, P]),
     "sgs_gemm": (I32, [P, I64, I64, P, I64, I64, P, I64, I64, I64, I64, I32, I32, P]),

@@ -1124,6 +1124,21 @@ int32_t sgs_gcn_edge_grad_partial(const int32_t* rowptr_dst, const int32_t* perm
                         G, h, dis, nullptr, loopw, M, N, D, tmp_g, tmp_t, tmp_a, nullptr, 0, as_stream(stream));
 }
 
+int32_t sgs_gcn_edge_grad_partial_h16(const int32_t* rowptr_dst, const int32_t* perm_dst, const int32_t* nbr_dst,
+                                      const float* what_dst, const int32_t* order_dst, const int32_t* rowptr_src,
+                                      const int32_t* perm_src, const float* G, const void* h16, const float* tscale,
+                                      const float* dis, const float* loopw, int64_t M, int64_t N, int64_t D,
+                                      float* tmp_g, float* tmp_t, float* tmp_a, sgs_stream_t stream) {
+  SGS_CHECK_ARG(N > 0 && M > 0 && D > 0, "bad sizes");
+  SGS_CHECK_ARG(rowptr_dst && perm_dst && nbr_dst && what_dst && rowptr_src && perm_src && G && h16 && tscale && dis &&
+                    loopw && tmp_g && tmp_t && tmp_a,
+                "null pointer");
+  SGS_CHECK_ARG((((uintptr_t)h16 | (uintptr_t)G) & 15) == 0, "G / h16 must be 16-byte aligned");
+  return edge_grad_impl(1, rowptr_dst, perm_dst, nbr_dst, what_dst, order_dst, rowptr_src, perm_src, nullptr, nullptr,
+                        G, nullptr, dis, nullptr, loopw, M, N, D, tmp_g, tmp_t, tmp_a, nullptr, 0, as_stream(stream),
+                        h16, tscale);
+}
+
 int32_t sgs_gcn_edge_grad_final(const int32_t* src, const int32_t* dst, const float* tmp_g, const float* tmp_a,
                                 const float* dis, const float* deg, int64_t M, float* dw, int32_t accumulate,
                                 sgs_stream_t stream) {

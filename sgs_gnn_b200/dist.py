@@ -254,9 +254,12 @@ def allreduce_grads(params, average=True):
     ps = [p for p in params if p.requires_grad]
     if not ps:
         return
-    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in ps], dtype=torch.float32, device=ps[0].device)
+    # the bitmap is assembled from two device scalars inside the same cat: no host->device copy (a pageable upload
+    # synchronises the stream, a pinned one queues behind the loader's prefetch on the copy engine)
+    dev = ps[0].device
+    one, zero = torch.ones(1, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.float32, device=dev)
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
-                      for p in ps] + [has])
+                      for p in ps] + [zero if p.grad is None else one for p in ps])
     staged = flat.is_cuda and dist.get_backend() == "gloo"
     if staged:
         c = flat.cpu()

@@ -467,7 +467,8 @@ class ShardedGCNConvFn(torch.autograd.Function):
                 ops.linear_nt_into(x[lo:hi], weight, h[lo:hi])
             lg.comm.exchange_rows(h, lg.bounds)
         stage = lg.comm.peer_stage(n, d) if (exchange_out and lg.comm.world > 1) else None
-        out = ops.spmm(g.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed, table=ops.gather_table(h),
+        tab = ops.gather_table(h)
+        out = ops.spmm(g.csr_dst, norm.what_dst, norm, h, bias, relu, p_drop, seed, table=tab,
                        rows=(lo, hi), peers=(lg.comm, stage) if stage is not None else None)
         if stage is not None:
             lg.comm.peer_finish_exchange(out, lg.bounds, stage, pushed=True)
@@ -475,6 +476,7 @@ class ShardedGCNConvFn(torch.autograd.Function):
             lg.comm.exchange_rows(out, lg.bounds)
         ctx.lg, ctx.norm, ctx.relu, ctx.p_drop, ctx.exchange_out = lg, norm, relu, p_drop, exchange_out
         ctx.has_w = edge_weight is not None
+        ctx.tab = tab if ctx.has_w else None       # the edge-weight gradient gathers the same rows of h
         ctx.save_for_backward(x, weight, h if ctx.has_w else None, out if relu else None)
         return out
 
@@ -538,11 +540,19 @@ class ShardedGCNConvFn(torch.autograd.Function):
             rp_d, pm_d, nb_d, od_d = g.csr_dst
             rp_s, pm_s, _, _ = g.csr_src
             with _timed(f"edge_grad_d{d}"):
-                if m > 0:
+                if m > 0 and ctx.tab is not None:
+                    check(lib().sgs_gcn_edge_grad_partial_h16(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst),
+                                                              _p(od_d), _p(rp_s), _p(pm_s), _p(g_full),
+                                                              _p(ctx.tab.data), _p(ctx.tab.scale), _p(norm.dis),
+                                                              _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]),
+                                                              _p(tmp[2 * m:]), _stream()),
+                          "sgs_gcn_edge_grad_partial_h16")
+                elif m > 0:
                     check(lib().sgs_gcn_edge_grad_partial(_p(rp_d), _p(pm_d), _p(nb_d), _p(norm.what_dst), _p(od_d),
                                                           _p(rp_s), _p(pm_s), _p(g_full), _p(h), _p(norm.dis),
                                                           _p(norm.loopw), m, n, d, _p(tmp), _p(tmp[m:]),
                                                           _p(tmp[2 * m:]), _stream()), "sgs_gcn_edge_grad_partial")
+            ctx.tab = None
             comm.all_reduce(tmp[2 * m:])
             if m > 0:
                 check(lib().sgs_gcn_edge_grad_final(_p(g.src), _p(g.dst), _p(tmp), _p(tmp[2 * m:]), _p(norm.dis),
@@ -707,9 +717,12 @@ def allreduce_partial_grads(params, comm):
     if not ps:
         return
     dev = ps[0].device
-    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in ps], dtype=torch.float32, device=dev)
+    # the bitmap is assembled from two device scalars inside the same cat: no host->device copy (a pageable upload
+    # synchronises the stream, a pinned one queues behind the loader's prefetch on the copy engine)
+    dev = ps[0].device
+    one, zero = torch.ones(1, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.float32, device=dev)
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
-                      for p in ps] + [has])
+                      for p in ps] + [zero if p.grad is None else one for p in ps])
     comm.all_reduce(flat)
     # the bitmap is only read (one small D2H) when some local gradient is None; the usual learned-wins step has none
     seen = flat[-len(ps):].cpu() if any(p.grad is None for p in ps) else None

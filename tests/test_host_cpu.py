@@ -46,3 +46,37 @@ def test_deferred_checks_raise_like_the_reference():
         _train_core._read_loss_and_checks(loss, [("sampler", torch.tensor([0, 0, 0, 0, 0, 0, 0, 6]))], 7)
     with pytest.raises(RuntimeError, match="outside"):
         _train_core._read_loss_and_checks(loss, [("oob", torch.ones(1, dtype=torch.int32))], 7)
+
+
+def test_bench_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path):
+    """bench.py's ClockSampler: samples carry nvidia-smi timestamps; only those inside [begin, end] count, and a
+    region too short to hold one falls back to the warm-up steps just before it (and says so)."""
+    import datetime
+    import importlib.util
+    import os
+    import time
+    spec = importlib.util.spec_from_file_location("sgs_bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    now = time.time()
+
+    def write(path):
+        with open(path, "w") as fh:
+            for i in range(10):
+                ts = datetime.datetime.fromtimestamp(now - 1 + 0.1 * i).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+                cap = "Active" if i == 7 else "Not Active"
+                fh.write(f"{ts}, {1900 + i}, 1965, 800.1, Not Active, Not Active, Not Active, {cap}\n")
+
+    c = bench.ClockSampler(0)
+    c.path = str(tmp_path / "a.csv")
+    write(c.path)
+    c.t0, c.t1 = now - 0.45, now - 0.28
+    out = c.summary()
+    assert out["window"] == "timed" and out["samples"] == 2 and out["sm_mhz"] == 1906.5
+    assert out["reasons"] == ["sw_power_cap"] and out["sm_max_mhz"] == 1965.0
+    c = bench.ClockSampler(0)
+    c.path = str(tmp_path / "b.csv")
+    write(c.path)
+    c.t0, c.t1 = now + 0.5, now + 0.52           # nothing inside: the 3 s before it
+    out = c.summary()
+    assert out["window"] == "warmup+timed" and out["samples"] == 10
