@@ -68,31 +68,51 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.path = None
+        self.path = None        # (tests: a csv file to parse instead of a live child)
+        self.lines = []
+        self.cmd = None         # (tests: a stand-in for nvidia-smi)
         self.t0 = self.t1 = None
 
     def __enter__(self):
         if os.environ.get("SGS_NO_CLOCKS") or self.index is None:
             return self
         try:
-            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
-                                         stderr=subprocess.DEVNULL)
+            # on a pseudo-terminal, so that nvidia-smi line-buffers: into a file or a pipe its stdio buffer holds ~4 KB
+            # (seconds of samples) back and loses them when the child is terminated
+            import pty
+            import threading
+            master, slave = pty.openpty()
+            cmd = self.cmd or ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                               "--format=csv,noheader,nounits", "-lms", "100"]
+            self.proc = subprocess.Popen(cmd, stdout=slave, stdin=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                                         close_fds=True)
+            os.close(slave)
+
+            def pump():
+                buf = b""
+                while True:
+                    try:
+                        chunk = os.read(master, 4096)
+                    except OSError:
+                        break
+                    if not chunk:
+                        break
+                    buf += chunk
+                    *done, buf = buf.split(b"\n")
+                    self.lines.extend(ln.decode("ascii", "replace").strip() for ln in done)
+                os.close(master)
+
+            threading.Thread(target=pump, daemon=True).start()
         except Exception:
             self.proc = None
         return self
 
     def wait_ready(self, timeout=8.0):
-        """Block (before the timed region) until the child has written its first sample."""
+        """Block (before the timed region) until the child has delivered its first sample."""
         t_end = time.time() + timeout
         while self.proc is not None and self.proc.poll() is None and time.time() < t_end:
-            try:
-                if os.path.getsize(self.path) > 0:
-                    return True
-            except OSError:
-                pass
+            if self.lines:
+                return True
             time.sleep(0.05)
         return False
 
@@ -120,11 +140,12 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.path or not os.path.isfile(self.path):
-            return out
+        lines = list(self.lines)
+        if self.path and os.path.isfile(self.path):
+            lines += open(self.path).read().splitlines()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = []
-        for line in open(self.path):
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -148,10 +169,6 @@ class ClockSampler:
             out["samples"] = len(inside)
             out["window"] = window
             out["reasons"] = sorted({n for r in inside for n in r[3]})
-        try:
-            os.unlink(self.path)
-        except OSError:
-            pass
         return out
 
 
@@ -367,6 +384,12 @@ def run_gpu_arm(a):
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(gemm=a.gemm_precision, scorer=a.precision, gather=a.gather_precision)
     _lib.lib()
+    # host placement: the main thread (kernel launches, pinned allocations of the e2e arm) moves to the CPUs nearest
+    # this GPU; the intra-op pool is created first, on the full mask, for the cpu_baseline leg
+    orig_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    torch.randn(1 << 22).sum()
+    from sgs_gnn_b200 import loader as sloader
+    bound_cpus = sloader.bind_host_to_gpu(dev)
     # rank 0's GPU is the one reported; started here because nvidia-smi needs seconds to come up on an 8-GPU box
     clk = ClockSampler(local if rank == 0 else None).__enter__()
 
@@ -563,7 +586,8 @@ def run_gpu_arm(a):
                "d2h_bytes_per_step": 32 * 8 + 4, "ms_per_step": ms_e / a.steps,
                "how": f"one train() call over {a.steps} pinned host batches ({a.host_index} edge_index); the loop "
                       "uploads batch k+1 on a copy stream while step k computes (double-buffered device batch); "
-                      "every step's inputs cross PCIe inside the timed region",
+                      "every step's inputs cross PCIe inside the timed region; host thread and pinned memory on the "
+                      f"GPU's NUMA node ({len(bound_cpus) if bound_cpus else 'unbound'} cpus)",
                "serial_ms_per_step": ms_serial}
         del host, loader_h
 
@@ -643,6 +667,8 @@ def run_gpu_arm(a):
 
     cpu = None
     if not a.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only (rank 0 is the only rank there)
+        if orig_affinity is not None:
+            os.sched_setaffinity(0, orig_affinity)      # every host core again
         cpu = host_baseline(a, 2, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

@@ -78,3 +78,28 @@ def copy_fields_async(fields, dev, stream):
             if v is not None:
                 out[k].copy_(v, non_blocking=True)
     return out
+
+
+def bind_host_to_gpu(device=None):
+    """Pin the calling thread (and the threads it starts later) to the CPUs NVML reports as nearest to `device`, so
+    that pinned host batches allocated afterwards are first-touched on the GPU's NUMA node and the launching thread
+    does not migrate across sockets.  (The one-GPU box of this pool is a single-node 16-vCPU VM, where this is a
+    no-op; its upload rate still varies 18-36 GB/s run to run.)  Returns the CPU set applied, or None when NVML / the
+    affinity call is not available (never an error: this is a placement hint)."""
+    try:
+        import pynvml
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(idx).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        near = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus = near & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None

@@ -80,3 +80,26 @@ def test_bench_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path):
     c.t0, c.t1 = now + 0.5, now + 0.52           # nothing inside: the 3 s before it
     out = c.summary()
     assert out["window"] == "warmup+timed" and out["samples"] == 10
+
+
+def test_bench_clock_sampler_reads_a_live_child_line_by_line():
+    """The child writes to a pseudo-terminal, so every sample arrives as soon as it is printed (a file or pipe would
+    hold ~4 KB back and lose it at terminate)."""
+    import importlib.util
+    import os
+    import time
+    spec = importlib.util.spec_from_file_location("sgs_bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.ClockSampler(0)
+    c.cmd = ["sh", "-c", 'while true; do echo "$(date "+%Y/%m/%d %H:%M:%S.%3N"), 1900, 1965, 800.0, Not Active, '
+             'Not Active, Not Active, Active"; sleep 0.05; done']
+    with c:
+        assert c.wait_ready(5.0)
+        c.begin()
+        time.sleep(0.4)
+        c.end()
+    out = c.summary()
+    assert out["window"] == "timed" and out["samples"] >= 3 and out["sm_mhz"] == 1900.0
+    assert out["reasons"] == ["sw_power_cap"]
+    assert c.proc.poll() is not None        # the child is gone
