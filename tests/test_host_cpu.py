@@ -103,3 +103,13 @@ def test_bench_clock_sampler_reads_a_live_child_line_by_line():
     assert out["window"] == "timed" and out["samples"] >= 3 and out["sm_mhz"] == 1900.0
     assert out["reasons"] == ["sw_power_cap"]
     assert c.proc.poll() is not None        # the child is gone
+
+
+def test_bind_host_to_gpu_is_a_hint_not_an_error():
+    """Without a GPU / NVML the placement helper reports None and leaves the affinity alone."""
+    import os
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert loader.bind_host_to_gpu("cuda:0") is None
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
