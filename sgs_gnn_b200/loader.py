@@ -6,7 +6,8 @@ batch k+1 on a separate CUDA stream while step k computes, into freshly allocate
 construction: batch k stays alive until its step drops it).  Batches that already live on the device pass through.
 
 Host batches may carry `edge_index` as int32 [2, E] (`Batch.compact()`): node ids fit 31 bits, so the int64 form of
-the reference only doubles the bytes on the host link; ops.Graph takes the int32 rows as they are.
+the reference only doubles the bytes on the host link; ops.Graph takes the int32 rows as they are.  A source-sorted edge
+list additionally sends its source row as the CSR row pointer (N + 1 ints), rebuilt on the device during the upload.
 """
 from __future__ import annotations
 

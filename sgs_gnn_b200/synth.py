@@ -53,27 +53,64 @@ class Batch:
 
     def pin_memory(self):
         kw = {k: getattr(self, k).pin_memory() for k in self._FIELDS if getattr(self, k) is not None}
-        return Batch(num_classes=self.num_classes, **kw)
+        out = Batch(num_classes=self.num_classes, **kw)
+        if getattr(self, "_src_rowptr", None) is not None:
+            out._src_rowptr = self._src_rowptr.pin_memory()
+            out._dst_row = out.edge_index[1]           # (a view of the pinned edge_index)
+        return out
 
-    def compact(self):
+    def compact(self, rowptr=True):
         """Same batch with `edge_index` narrowed to int32 [2, E] (node ids fit 31 bits): half the bytes on the host
-        link; ops.Graph uses the int32 rows as they are (the reference's int64 form stays supported everywhere)."""
+        link; ops.Graph uses the int32 rows as they are (the reference's int64 form stays supported everywhere).
+        rowptr: when the edge list is sorted by source (coalesced PyG datasets are), `upload_async` sends the source
+        row as its CSR row pointer (N + 1 ints instead of E) and rebuilds it on the device, bit for bit."""
         kw = {k: getattr(self, k) for k in self._FIELDS if getattr(self, k) is not None}
         if kw["edge_index"].dtype != torch.int32:
             if self.num_nodes >= 2 ** 31:
                 raise RuntimeError("node ids do not fit int32")
             kw["edge_index"] = kw["edge_index"].to(torch.int32)
-        return Batch(num_classes=self.num_classes, **kw)
+        out = Batch(num_classes=self.num_classes, **kw)
+        ei = out.edge_index
+        e, n = ei.size(1), self.num_nodes
+        if rowptr and ei.device.type == "cpu" and 0 < e < 2 ** 31 and e > n + 1:
+            src = ei[0]
+            if bool((src[1:] >= src[:-1]).all()) and int(src[0]) >= 0 and int(src[-1]) < n:
+                nodes = torch.arange(n + 1, dtype=torch.int32)
+                out._src_rowptr = torch.searchsorted(src, nodes, right=False).to(torch.int32)
+                out._dst_row = ei[1]
+        return out
 
     def upload_async(self, dev, stream):
         """Device copy whose H2D transfers are enqueued on `stream` (see loader.prefetch)."""
         from .loader import copy_fields_async
-        kw = copy_fields_async({k: getattr(self, k) for k in self._FIELDS}, dev, stream)
+        rp = getattr(self, "_src_rowptr", None)
+        fields = {k: getattr(self, k) for k in self._FIELDS}
+        if rp is not None:
+            fields["edge_index"] = None
+        kw = copy_fields_async(fields, dev, stream)
+        if rp is not None:
+            e, n = self.edge_index.size(1), self.num_nodes
+            ei = torch.empty(2, e, dtype=torch.int32, device=dev)
+            with torch.cuda.stream(stream):
+                ei[1].copy_(self._dst_row, non_blocking=True)
+                rp_d = rp.to(dev, non_blocking=True)
+                deg = (rp_d[1:] - rp_d[:-1]).to(torch.int64)
+                ei[0].copy_(torch.repeat_interleave(torch.arange(n, dtype=torch.int32, device=dev), deg,
+                                                    output_size=e))
+            kw["edge_index"] = ei
         return Batch(num_classes=self.num_classes, **{k: v for k, v in kw.items() if v is not None})
 
     def nbytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size()
                    for k in self._FIELDS if getattr(self, k) is not None)
+
+    def upload_nbytes(self):
+        """Bytes `upload_async` sends over the host link."""
+        nb = self.nbytes()
+        rp = getattr(self, "_src_rowptr", None)
+        if rp is not None:
+            nb += rp.numel() * rp.element_size() - self.edge_index[0].numel() * self.edge_index.element_size()
+        return nb
 
 
 def _weighted_pick(cdf, u):

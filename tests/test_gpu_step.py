@@ -157,6 +157,25 @@ def test_prefetched_int32_host_batches_match_resident_training(dev):
         assert float((pa - pb).abs().max()) < 5e-3 * (1.0 + float(pa.abs().max()))
 
 
+@pytest.mark.gpu
+def test_row_pointer_upload_rebuilds_edge_index_bit_for_bit(dev):
+    """Batch.compact() sends a source-sorted edge list as (row pointer, destination row); loader.prefetch must hand
+    the step the identical int32 edge_index, and the same for an unsorted list (plain form)."""
+    from sgs_gnn_b200 import loader, synth
+    b = synth.make_graph(None, seed=9, n=3000, e=80000, f=8, c=3)
+    for flip in (False, True):
+        if flip:
+            b.edge_index = b.edge_index.flip(1)
+        host = b.compact().pin_memory()
+        assert (getattr(host, "_src_rowptr", None) is None) == flip
+        got = list(loader.prefetch([host, host], dev))
+        torch.cuda.synchronize()
+        for g in got:
+            assert g.edge_index.dtype == torch.int32 and g.edge_index.is_cuda
+            assert torch.equal(g.edge_index.cpu().long(), b.edge_index)
+            assert torch.equal(g.x.cpu(), b.x) and torch.equal(g.prob.cpu(), b.prob)
+
+
 @pytest.mark.parametrize("mode", ["full", "edge"])
 def test_baseline_modes_match_reference_training(dev, mode, monkeypatch):
     """the `full` / `edge` baseline modes of training_hybrid.train (:149-180) with the `optimizer` of

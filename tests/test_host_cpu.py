@@ -113,3 +113,17 @@ def test_bind_host_to_gpu_is_a_hint_not_an_error():
         assert loader.bind_host_to_gpu("cuda:0") is None
     assert os.sched_getaffinity(0) <= before
     os.sched_setaffinity(0, before)
+
+
+def test_compact_sends_a_sorted_source_row_as_its_row_pointer():
+    b = synth.make_graph(None, seed=3, n=60, e=400, f=4, c=2)
+    c = b.compact()
+    rp = c._src_rowptr
+    assert rp.dtype == torch.int32 and rp.numel() == 61 and int(rp[0]) == 0 and int(rp[-1]) == 400
+    deg = (rp[1:] - rp[:-1]).to(torch.int64)
+    src = torch.repeat_interleave(torch.arange(60, dtype=torch.int32), deg, output_size=400)
+    assert torch.equal(src, c.edge_index[0])
+    assert c.upload_nbytes() == c.nbytes() - 400 * 4 + 61 * 4
+    assert b.compact(rowptr=False).upload_nbytes() == c.nbytes()
+    b.edge_index = b.edge_index.flip(1)            # not sorted by source: the plain int32 form
+    assert getattr(b.compact(), "_src_rowptr", None) is None
