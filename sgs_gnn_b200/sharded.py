@@ -716,7 +716,6 @@ def allreduce_partial_grads(params, comm):
     ps = [p for p in params if p.requires_grad]
     if not ps:
         return
-    dev = ps[0].device
     # the bitmap is assembled from two device scalars inside the same cat: no host->device copy (a pageable upload
     # synchronises the stream, a pinned one queues behind the loader's prefetch on the copy engine)
     dev = ps[0].device
