@@ -54,6 +54,23 @@ def run(rank, world, port, pipeline, conditional, edge_mlp, n, e, f, c, hdim):
         comm = sharded.Comm()
         sb = sharded.ShardedBatch(b, comm)
         assert sb.bounds[0] == 0 and sb.bounds[-1] == n
+
+        # ---- the prefetching loader's compact upload (int32 gid, source row as row pointer) is bit-exact ----
+        from sgs_gnn_b200 import loader
+        plain = sb.to("cpu")
+        host = plain.compact().pin_memory()
+        assert host._gid32 is not None and host._src_rowptr is not None and host.edge_index.dtype == torch.int32
+        e_loc = sb.edge_index.size(1)
+        if comm.staged:     # (over NCCL only this rank's slice of x crosses the host link)
+            assert host.upload_nbytes() == plain.nbytes() - 16 * e_loc + 4 * (n + 1)
+        for up in loader.prefetch([host, host], dev):
+            torch.cuda.synchronize()
+            for k in sb._TENSORS:
+                want_t, got_t = getattr(sb, k), getattr(up, k)
+                if k == "edge_index":
+                    assert got_t.dtype == torch.int32 and torch.equal(got_t.long(), want_t.long()), k
+                else:
+                    assert got_t.dtype == want_t.dtype and torch.equal(got_t, want_t), k
         for trial, (pv, nz) in enumerate([(torch.rand(b.num_edges, generator=g).to(dev), noise[0]),
                                           ((torch.round(torch.rand(b.num_edges, generator=g) * 3) / 3 + 0.1).to(dev),
                                            torch.ones(b.num_edges, device=dev))]):
